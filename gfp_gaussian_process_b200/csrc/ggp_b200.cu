@@ -1,0 +1,466 @@
+// ggp_b200.cu — C ABI of libggp_b200.so (include/ggp_b200.h): host-side flattening of the lineage forest
+// into generation-ordered device arrays, launch sequencing, and result hand-back.
+//
+// Host side of what the reference does in moma_input.h:125-189 (genealogy, roots), likelihood.h:110-174
+// (depth-first evaluation order; here only used to report the first NaN and to order nothing else) and
+// main.cpp:115-145 (forward, backward, combine).  No CPU compute path exists in this library: every
+// numerical result comes from the kernels in ggp_kernels.cuh.
+//
+// Build: nvcc -std=c++17 -O3 -fmad=false -gencode arch=compute_100a,code=sm_100a -lineinfo -shared
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/ggp_b200.h"
+#include "ggp_layout.hpp"
+#include "ggp_kernels.cuh"
+#include "ggp_joints.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define GGP_CUDA(call)                                                                             \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(e_ == cudaErrorMemoryAllocation ? GGP_ERR_NOMEM : GGP_ERR_CUDA,            \
+                        std::string(#call) + ": " + cudaGetErrorString(e_));                       \
+    } while (0)
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t ensure(size_t count) {
+        if (count <= n) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    cudaError_t upload(const std::vector<T>& h, cudaStream_t s) {
+        cudaError_t e = ensure(h.size());
+        if (e != cudaSuccess) return e;
+        return cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+
+}  // namespace
+
+struct ggp_forest {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int64_t n_cells = 0, n_ctp = 0;
+    int32_t n_roots = 0, n_gen = 0, max_seg = 0;
+    GgpModel model{};
+    GgpLayout L;                          // host topology
+    std::vector<int32_t> gen_partial0;    // [n_gen+1] first block partial of each generation
+    // device
+    DevBuf<double> time, x, g;
+    DevBuf<int32_t> seg, comb_seg;
+    DevBuf<int64_t> s_off, s_dfs0;
+    DevBuf<int32_t> s_n, s_parent, s_d1, s_d2, s_root, s_cell;
+    // workspaces
+    DevBuf<double> w_params, w_state, w_partial, w_out, w_cell_ll, w_carry;
+    DevBuf<unsigned long long> w_nan;
+    DevBuf<double> fwd, bwd, comb, bstate, pred_params;
+    bool have_pred = false;
+    int32_t pred_n_seg = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double last_ms = 0.0;
+    int64_t last_launches = 0;
+    int64_t state_budget_bytes = (int64_t)8 << 30;
+
+    GgpDevForest dev() const {
+        GgpDevForest F;
+        F.n_cells = n_cells; F.n_ctp = n_ctp;
+        F.time = time.p; F.x = x.p; F.g = g.p; F.seg = seg.p;
+        F.s_off = s_off.p; F.s_n = s_n.p; F.s_parent = s_parent.p; F.s_d1 = s_d1.p; F.s_d2 = s_d2.p;
+        F.s_root = s_root.p; F.s_cell = s_cell.p; F.s_dfs0 = s_dfs0.p;
+        F.model = model;
+        for (int i = 0; i < 4; ++i) { F.init_f[i] = L.init_f[i]; F.init_r[i] = L.init_r[i]; }
+        return F;
+    }
+};
+
+namespace {
+
+int check_handle(const ggp_forest* f) {
+    if (!f) return fail(GGP_ERR_BAD_ARG, "null forest handle");
+    return GGP_OK;
+}
+
+int grid_of(int64_t n) { return (int)((n + GGP_BLOCK - 1) / GGP_BLOCK); }
+
+}  // namespace
+
+extern "C" {
+
+const char* ggp_last_error(void) { return g_err.c_str(); }
+const char* ggp_version(void) { return "ggp-b200 0.1 (sm_100a, fp64 strict)"; }
+
+int ggp_forest_create(const ggp_forest_desc* d, ggp_forest** out) {
+    if (!d || !out) return fail(GGP_ERR_BAD_ARG, "null argument");
+    *out = nullptr;
+    ggp_forest* f = new ggp_forest();
+    const std::string why = f->L.build(d);
+    if (!why.empty()) {
+        delete f;
+        return fail(GGP_ERR_BAD_ARG, why);
+    }
+    int dev_count = 0;
+    cudaError_t e = cudaGetDeviceCount(&dev_count);
+    if (e != cudaSuccess || d->device < 0 || d->device >= dev_count) {
+        delete f;
+        return fail(GGP_ERR_CUDA, e != cudaSuccess ? std::string("no CUDA device: ") + cudaGetErrorString(e) : "no such CUDA device");
+    }
+    e = cudaSetDevice(d->device);
+    const GgpLayout& L = f->L;
+    f->device = d->device;
+    f->n_cells = L.n_cells;
+    f->n_ctp = L.n_ctp;
+    f->n_roots = L.n_roots;
+    f->n_gen = L.n_gen;
+    f->max_seg = L.max_seg;
+    f->model.noise_scaled = d->noise_model == GGP_NOISE_SCALED;
+    f->model.division_binomial = d->division_model == GGP_DIVISION_BINOMIAL;
+    f->model.fp_auto = d->fp_auto;
+    f->gen_partial0.assign(L.n_gen + 1, 0);
+    for (int g = 0; g < L.n_gen; ++g)
+        f->gen_partial0[g + 1] = f->gen_partial0[g] + grid_of(L.gen_start[g + 1] - L.gen_start[g]);
+
+    cudaStream_t s = nullptr;
+    auto up_d = [&](DevBuf<double>& b, const double* h, int64_t n) {
+        if (e != cudaSuccess) return;
+        e = b.ensure(n);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(b.p, h, n * sizeof(double), cudaMemcpyHostToDevice, s);
+    };
+    up_d(f->time, d->time, d->n_ctp);
+    up_d(f->x, d->log_length, d->n_ctp);
+    up_d(f->g, d->fp, d->n_ctp);
+    if (e == cudaSuccess) e = f->seg.upload(L.seg, s);
+    if (e == cudaSuccess) e = f->comb_seg.upload(L.comb_seg, s);
+    if (e == cudaSuccess) e = f->s_off.upload(L.s_off, s);
+    if (e == cudaSuccess) e = f->s_dfs0.upload(L.s_dfs0, s);
+    if (e == cudaSuccess) e = f->s_n.upload(L.s_n, s);
+    if (e == cudaSuccess) e = f->s_parent.upload(L.s_parent, s);
+    if (e == cudaSuccess) e = f->s_d1.upload(L.s_d1, s);
+    if (e == cudaSuccess) e = f->s_d2.upload(L.s_d2, s);
+    if (e == cudaSuccess) e = f->s_root.upload(L.s_root, s);
+    if (e == cudaSuccess) e = f->s_cell.upload(L.s_cell, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e == cudaSuccess) e = cudaEventCreate(&f->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&f->ev1);
+    if (e != cudaSuccess) {
+        ggp_forest_destroy(f);
+        return fail(e == cudaErrorMemoryAllocation ? GGP_ERR_NOMEM : GGP_ERR_CUDA,
+                    std::string("forest upload: ") + cudaGetErrorString(e));
+    }
+    *out = f;
+    return GGP_OK;
+}
+
+void ggp_forest_destroy(ggp_forest* f) {
+    if (!f) return;
+    cudaSetDevice(f->device);
+    cudaDeviceSynchronize();
+    for (DevBuf<double>* b : {&f->time, &f->x, &f->g, &f->w_params, &f->w_state, &f->w_partial, &f->w_out, &f->w_cell_ll,
+                              &f->w_carry, &f->fwd, &f->bwd, &f->comb, &f->bstate, &f->pred_params})
+        b->release();
+    for (DevBuf<int32_t>* b : {&f->seg, &f->comb_seg, &f->s_n, &f->s_parent, &f->s_d1, &f->s_d2, &f->s_root, &f->s_cell})
+        b->release();
+    f->s_off.release();
+    f->s_dfs0.release();
+    f->w_nan.release();
+    if (f->ev0) cudaEventDestroy(f->ev0);
+    if (f->ev1) cudaEventDestroy(f->ev1);
+    delete f;
+}
+
+int ggp_forest_set_stream(ggp_forest* f, void* cuda_stream) {
+    if (int rc = check_handle(f)) return rc;
+    f->stream = (cudaStream_t)cuda_stream;
+    return GGP_OK;
+}
+
+int ggp_forest_upload_series(ggp_forest* f, const double* time, const double* log_length, const double* fp) {
+    if (int rc = check_handle(f)) return rc;
+    if (!time || !log_length || !fp) return fail(GGP_ERR_BAD_ARG, "null series");
+    GGP_CUDA(cudaSetDevice(f->device));
+    const size_t b = f->n_ctp * sizeof(double);
+    GGP_CUDA(cudaMemcpyAsync(f->time.p, time, b, cudaMemcpyHostToDevice, f->stream));
+    GGP_CUDA(cudaMemcpyAsync(f->x.p, log_length, b, cudaMemcpyHostToDevice, f->stream));
+    GGP_CUDA(cudaMemcpyAsync(f->g.p, fp, b, cudaMemcpyHostToDevice, f->stream));
+    f->have_pred = false;
+    return GGP_OK;
+}
+
+int64_t ggp_forest_n_cells(const ggp_forest* f) { return f ? f->n_cells : -1; }
+int64_t ggp_forest_n_ctp(const ggp_forest* f) { return f ? f->n_ctp : -1; }
+int64_t ggp_forest_n_roots(const ggp_forest* f) { return f ? f->n_roots : -1; }
+int64_t ggp_forest_n_generations(const ggp_forest* f) { return f ? f->n_gen : -1; }
+
+int ggp_forest_get_init(const ggp_forest* f, double* init_f4, double* init_r4) {
+    if (int rc = check_handle(f)) return rc;
+    for (int i = 0; i < 4; ++i) {
+        if (init_f4) init_f4[i] = f->L.init_f[i];
+        if (init_r4) init_r4[i] = f->L.init_r[i];
+    }
+    return GGP_OK;
+}
+
+double ggp_last_kernel_ms(const ggp_forest* f) { return f ? f->last_ms : -1.0; }
+int64_t ggp_last_launch_count(const ggp_forest* f) { return f ? f->last_launches : -1; }
+
+}  // extern "C"
+
+namespace {
+
+// enqueue the likelihood of vectors [0, n_vec) held in d_params; results to d_out [n_vec]
+int enqueue_loglik(ggp_forest* f, const double* d_params, int32_t n_vec, double* d_carry, double* d_out,
+                   double* d_cell_ll, unsigned long long* d_nan) {
+    const int64_t N = f->n_cells;
+    int64_t chunk = std::max<int64_t>(1, f->state_budget_bytes / (N * 14 * (int64_t)sizeof(double)));
+    chunk = std::min<int64_t>(chunk, n_vec);
+    chunk = std::min<int64_t>(chunk, 65535);
+    const int n_partial = f->gen_partial0[f->n_gen];
+    GGP_CUDA(f->w_state.ensure((size_t)chunk * N * 14));
+    GGP_CUDA(f->w_partial.ensure((size_t)chunk * n_partial));
+    const GgpDevForest F = f->dev();
+    for (int32_t v0 = 0; v0 < n_vec; v0 += (int32_t)chunk) {
+        const int32_t vc = (int32_t)std::min<int64_t>(chunk, n_vec - v0);
+        for (int g = 0; g < f->n_gen; ++g) {
+            GgpFwdArgs A{};
+            A.slot0 = (int)f->L.gen_start[g];
+            A.n_slots = (int)(f->L.gen_start[g + 1] - f->L.gen_start[g]);
+            A.params = d_params;
+            A.v0 = v0;
+            A.v_count = vc;
+            A.carry = d_carry;
+            A.state = f->w_state.p;
+            A.partial = f->w_partial.p;
+            A.partial0 = f->gen_partial0[g];
+            A.n_partial = n_partial;
+            A.cell_ll = d_cell_ll;
+            A.nan_key = d_nan;
+            A.out_fwd = nullptr;
+            const int gx = grid_of(A.n_slots);
+            if (g == 0 && d_carry)
+                ggp_forward_kernel<false, true><<<dim3(gx, 1), GGP_BLOCK, 0, f->stream>>>(F, A);
+            else
+                ggp_forward_kernel<false, false><<<dim3(gx, vc), GGP_BLOCK, 0, f->stream>>>(F, A);
+            ++f->last_launches;
+        }
+        ggp_reduce_kernel<<<vc, 256, 0, f->stream>>>(f->w_partial.p, n_partial, d_out + v0);
+        ++f->last_launches;
+    }
+    GGP_CUDA(cudaGetLastError());
+    return GGP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ggp_loglik(ggp_forest* f, const double* params, int32_t n_vec, double* root_carry, double* out_loglik,
+               double* out_cell_ll, ggp_nan_info* nan) {
+    if (int rc = check_handle(f)) return rc;
+    if (!params || !out_loglik || n_vec <= 0) return fail(GGP_ERR_BAD_ARG, "bad params/out/n_vec");
+    GGP_CUDA(cudaSetDevice(f->device));
+    cudaStream_t s = f->stream;
+    GGP_CUDA(f->w_params.ensure((size_t)n_vec * GGP_NP));
+    GGP_CUDA(f->w_out.ensure(n_vec));
+    GGP_CUDA(f->w_nan.ensure(n_vec));
+    if (out_cell_ll) GGP_CUDA(f->w_cell_ll.ensure((size_t)n_vec * f->n_cells));
+    if (root_carry) {
+        GGP_CUDA(f->w_carry.ensure((size_t)f->n_roots * 16));
+        GGP_CUDA(cudaMemcpyAsync(f->w_carry.p, root_carry, (size_t)f->n_roots * 16 * sizeof(double), cudaMemcpyHostToDevice, s));
+    }
+    GGP_CUDA(cudaMemcpyAsync(f->w_params.p, params, (size_t)n_vec * GGP_NP * sizeof(double), cudaMemcpyHostToDevice, s));
+    GGP_CUDA(cudaMemsetAsync(f->w_nan.p, 0xff, (size_t)n_vec * sizeof(unsigned long long), s));
+    f->last_launches = 0;
+    GGP_CUDA(cudaEventRecord(f->ev0, s));
+    if (int rc = enqueue_loglik(f, f->w_params.p, n_vec, root_carry ? f->w_carry.p : nullptr, f->w_out.p,
+                                out_cell_ll ? f->w_cell_ll.p : nullptr, f->w_nan.p))
+        return rc;
+    GGP_CUDA(cudaEventRecord(f->ev1, s));
+    GGP_CUDA(cudaMemcpyAsync(out_loglik, f->w_out.p, (size_t)n_vec * sizeof(double), cudaMemcpyDeviceToHost, s));
+    std::vector<unsigned long long> keys(n_vec);
+    GGP_CUDA(cudaMemcpyAsync(keys.data(), f->w_nan.p, (size_t)n_vec * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    if (out_cell_ll)
+        GGP_CUDA(cudaMemcpyAsync(out_cell_ll, f->w_cell_ll.p, (size_t)n_vec * f->n_cells * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (root_carry)
+        GGP_CUDA(cudaMemcpyAsync(root_carry, f->w_carry.p, (size_t)f->n_roots * 16 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    GGP_CUDA(cudaStreamSynchronize(s));
+    float ms = 0.f;
+    GGP_CUDA(cudaEventElapsedTime(&ms, f->ev0, f->ev1));
+    f->last_ms = ms;
+    bool any_nan = false;
+    for (int32_t v = 0; v < n_vec; ++v) {
+        int64_t cell = -1, t = -1;
+        if (keys[v] != ~0ull) {
+            any_nan = true;
+            f->L.locate((int64_t)keys[v], &cell, &t);
+        }
+        if (nan) { nan[v].cell = cell; nan[v].t_index = t; }
+    }
+    if (any_nan) return fail(GGP_ERR_NAN, "Likelihood is Nan");
+    return GGP_OK;
+}
+
+int ggp_loglik_device(ggp_forest* f, const double* d_params, int32_t n_vec, double* d_out_loglik) {
+    if (int rc = check_handle(f)) return rc;
+    if (!d_params || !d_out_loglik || n_vec <= 0) return fail(GGP_ERR_BAD_ARG, "bad params/out/n_vec");
+    GGP_CUDA(cudaSetDevice(f->device));
+    GGP_CUDA(f->w_nan.ensure(n_vec));
+    GGP_CUDA(cudaMemsetAsync(f->w_nan.p, 0xff, (size_t)n_vec * sizeof(unsigned long long), f->stream));
+    f->last_launches = 0;
+    GGP_CUDA(cudaEventRecord(f->ev0, f->stream));
+    if (int rc = enqueue_loglik(f, d_params, n_vec, nullptr, d_out_loglik, nullptr, f->w_nan.p)) return rc;
+    GGP_CUDA(cudaEventRecord(f->ev1, f->stream));
+    return GGP_OK;
+}
+
+int ggp_sync_kernel_ms(ggp_forest* f, double* ms_out) {
+    if (int rc = check_handle(f)) return rc;
+    GGP_CUDA(cudaSetDevice(f->device));
+    GGP_CUDA(cudaEventSynchronize(f->ev1));
+    float ms = 0.f;
+    GGP_CUDA(cudaEventElapsedTime(&ms, f->ev0, f->ev1));
+    f->last_ms = ms;
+    if (ms_out) *ms_out = ms;
+    return GGP_OK;
+}
+
+int ggp_predict(ggp_forest* f, const double* params, int32_t n_seg, double* out_forward, double* out_backward,
+                double* out_combined) {
+    if (int rc = check_handle(f)) return rc;
+    if (!params || n_seg <= 0) return fail(GGP_ERR_BAD_ARG, "bad params/n_seg");
+    if (f->max_seg >= n_seg) return fail(GGP_ERR_BAD_ARG, "segment index exceeds the number of parameter sets");
+    GGP_CUDA(cudaSetDevice(f->device));
+    cudaStream_t s = f->stream;
+    const int64_t N = f->n_cells, M = f->n_ctp;
+    GGP_CUDA(f->pred_params.ensure((size_t)n_seg * GGP_NP));
+    GGP_CUDA(f->w_state.ensure((size_t)N * 14));
+    GGP_CUDA(f->fwd.ensure((size_t)M * 20));
+    GGP_CUDA(f->bwd.ensure((size_t)M * 20));
+    GGP_CUDA(f->comb.ensure((size_t)M * 20));
+    GGP_CUDA(f->bstate.ensure((size_t)N * 20));
+    GGP_CUDA(cudaMemcpyAsync(f->pred_params.p, params, (size_t)n_seg * GGP_NP * sizeof(double), cudaMemcpyHostToDevice, s));
+    f->pred_n_seg = n_seg;
+    f->have_pred = false;
+    f->last_launches = 0;
+    const GgpDevForest F = f->dev();
+    GGP_CUDA(cudaEventRecord(f->ev0, s));
+    for (int g = 0; g < f->n_gen; ++g) {
+        GgpFwdArgs A{};
+        A.slot0 = (int)f->L.gen_start[g];
+        A.n_slots = (int)(f->L.gen_start[g + 1] - f->L.gen_start[g]);
+        A.params = f->pred_params.p;
+        A.v0 = 0;
+        A.v_count = 1;
+        A.state = f->w_state.p;
+        A.out_fwd = f->fwd.p;
+        ggp_forward_kernel<true, false><<<dim3(grid_of(A.n_slots), 1), GGP_BLOCK, 0, s>>>(F, A);
+        ++f->last_launches;
+    }
+    for (int g = f->n_gen - 1; g >= 0; --g) {
+        GgpBwdArgs B{};
+        B.slot0 = (int)f->L.gen_start[g];
+        B.n_slots = (int)(f->L.gen_start[g + 1] - f->L.gen_start[g]);
+        B.params = f->pred_params.p;
+        B.fwd = f->fwd.p;
+        B.bwd = f->bwd.p;
+        B.bstate = f->bstate.p;
+        ggp_backward_kernel<<<grid_of(B.n_slots), GGP_BLOCK, 0, s>>>(F, B);
+        ++f->last_launches;
+    }
+    ggp_combine_kernel<<<grid_of(M), GGP_BLOCK, 0, s>>>(M, f->fwd.p, f->bwd.p, f->comb_seg.p, f->pred_params.p, f->comb.p);
+    ++f->last_launches;
+    GGP_CUDA(cudaGetLastError());
+    GGP_CUDA(cudaEventRecord(f->ev1, s));
+    const size_t bytes = (size_t)M * 20 * sizeof(double);
+    if (out_forward) GGP_CUDA(cudaMemcpyAsync(out_forward, f->fwd.p, bytes, cudaMemcpyDeviceToHost, s));
+    if (out_backward) GGP_CUDA(cudaMemcpyAsync(out_backward, f->bwd.p, bytes, cudaMemcpyDeviceToHost, s));
+    if (out_combined) GGP_CUDA(cudaMemcpyAsync(out_combined, f->comb.p, bytes, cudaMemcpyDeviceToHost, s));
+    GGP_CUDA(cudaStreamSynchronize(s));
+    float ms = 0.f;
+    GGP_CUDA(cudaEventElapsedTime(&ms, f->ev0, f->ev1));
+    f->last_ms = ms;
+    f->have_pred = true;
+    return GGP_OK;
+}
+
+int ggp_backward_cell_state(ggp_forest* f, double* out_cell_state20) {
+    if (int rc = check_handle(f)) return rc;
+    if (!f->have_pred) return fail(GGP_ERR_BAD_ARG, "ggp_predict has not been run on this handle");
+    if (!out_cell_state20) return fail(GGP_ERR_BAD_ARG, "null output");
+    GGP_CUDA(cudaSetDevice(f->device));
+    std::vector<double> tmp((size_t)f->n_cells * 20);
+    GGP_CUDA(cudaMemcpyAsync(tmp.data(), f->bstate.p, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
+    GGP_CUDA(cudaStreamSynchronize(f->stream));
+    for (int64_t s = 0; s < f->n_cells; ++s)
+        std::memcpy(out_cell_state20 + 20 * (int64_t)f->L.cell_of_slot[s], tmp.data() + 20 * s, 20 * sizeof(double));
+    return GGP_OK;
+}
+
+int ggp_math_eval(int32_t device, int32_t fn, int64_t n, const double* x, const double* y, double* out) {
+    if (!x || !out || n <= 0 || fn < 0 || fn > 3 || (fn == 2 && !y)) return fail(GGP_ERR_BAD_ARG, "bad argument");
+    GGP_CUDA(cudaSetDevice(device));
+    DevBuf<double> dx, dy, dout;
+    GGP_CUDA(dx.ensure(n));
+    GGP_CUDA(dy.ensure(n));
+    GGP_CUDA(dout.ensure(n));
+    GGP_CUDA(cudaMemcpy(dx.p, x, n * sizeof(double), cudaMemcpyHostToDevice));
+    if (y) GGP_CUDA(cudaMemcpy(dy.p, y, n * sizeof(double), cudaMemcpyHostToDevice));
+    ggp_math_kernel<<<grid_of(n), GGP_BLOCK>>>(fn, n, dx.p, dy.p, dout.p);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(out, dout.p, n * sizeof(double), cudaMemcpyDeviceToHost);
+    dx.release(); dy.release(); dout.release();
+    if (e != cudaSuccess) return fail(GGP_ERR_CUDA, cudaGetErrorString(e));
+    return GGP_OK;
+}
+
+int ggp_propagate_eval(int32_t device, int64_t n, const double* state14, const double* dt, const double* p7,
+                       double* out14, double* cross16) {
+    if (!state14 || !dt || !p7 || !out14 || n <= 0) return fail(GGP_ERR_BAD_ARG, "bad argument");
+    GGP_CUDA(cudaSetDevice(device));
+    DevBuf<double> ds, dd, dp, dout, dc;
+    GGP_CUDA(ds.ensure(14 * n));
+    GGP_CUDA(dd.ensure(n));
+    GGP_CUDA(dp.ensure(7 * n));
+    GGP_CUDA(dout.ensure(14 * n));
+    if (cross16) GGP_CUDA(dc.ensure(16 * n));
+    GGP_CUDA(cudaMemcpy(ds.p, state14, 14 * n * sizeof(double), cudaMemcpyHostToDevice));
+    GGP_CUDA(cudaMemcpy(dd.p, dt, n * sizeof(double), cudaMemcpyHostToDevice));
+    GGP_CUDA(cudaMemcpy(dp.p, p7, 7 * n * sizeof(double), cudaMemcpyHostToDevice));
+    ggp_propagate_kernel<<<grid_of(n), GGP_BLOCK>>>(n, ds.p, dd.p, dp.p, dout.p, cross16 ? dc.p : nullptr);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(out14, dout.p, 14 * n * sizeof(double), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && cross16) e = cudaMemcpy(cross16, dc.p, 16 * n * sizeof(double), cudaMemcpyDeviceToHost);
+    ds.release(); dd.release(); dp.release(); dout.release(); dc.release();
+    if (e != cudaSuccess) return fail(GGP_ERR_CUDA, cudaGetErrorString(e));
+    return GGP_OK;
+}
+
+}  // extern "C"
+
+#include "ggp_joints_host.inc"

@@ -1,0 +1,133 @@
+/* ggp_b200.h — C ABI of libggp_b200.so: the B200 (sm_100a, FP64) implementation of the lineage-tree
+ * likelihood / forward-backward / joints hot path of bjks/gfp_gaussian_process.
+ *
+ * The reference has no plugin or FFI interface; the seam is a set of free C++ functions that walk
+ * `std::vector<MOMAdata>` with raw pointers.  Each entry point below names the
+ * reference function it replaces (paths relative to the reference's src/).  Plain pointers and sizes
+ * only; no C++ or torch types; no exceptions cross this boundary (status codes + ggp_last_error()).
+ * INTEGRATION.md shows the binding a maintainer would add to the reference's likelihood.h/main.cpp.
+ *
+ * All host arrays stay owned by the caller and may be freed after the call that takes them returns.
+ * Calls on one handle must be serialised by the caller (the reference itself is single-threaded,
+ * likelihood.h:7-10).  There is NO CPU fallback: without a CUDA device every call returns
+ * GGP_ERR_CUDA.
+ */
+#ifndef GGP_B200_H
+#define GGP_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GGP_N_PARAMS 11   /* mean_lambda gamma_lambda var_lambda mean_q gamma_q var_q beta var_x var_g var_dx var_dg
+                             (likelihood.h:40-42, Parameters.h:175) */
+
+enum {
+    GGP_OK = 0,
+    GGP_ERR_BAD_ARG = 1,   /* reference: std::invalid_argument */
+    GGP_ERR_NAN = 2,       /* reference: std::domain_error("Likelihood is Nan"), likelihood.h:71-93 */
+    GGP_ERR_CUDA = 3,
+    GGP_ERR_NOMEM = 4
+};
+
+enum { GGP_NOISE_CONST = 0, GGP_NOISE_SCALED = 1 };       /* MOMAdata::noise_model, likelihood.h:59-64 */
+enum { GGP_DIVISION_GAUSS = 0, GGP_DIVISION_BINOMIAL = 1 }; /* MOMAdata::cell_division_model, predictions.h:40-60 */
+
+typedef struct ggp_forest ggp_forest;
+
+/* The data the path reads from std::vector<MOMAdata> (moma_input.h:22-80), flattened to SoA.
+ * Cells are in input-file order (that order defines daughter1/daughter2 and the depth-first
+ * evaluation order, moma_input.h:125-151, likelihood.h:110-122). */
+typedef struct {
+    int64_t n_cells;
+    int64_t n_ctp;               /* total cell-timepoints */
+    const int64_t* cell_offset;  /* [n_cells+1] */
+    const int32_t* parent;       /* [n_cells] index or -1 */
+    const int32_t* daughter1;    /* [n_cells] index or -1 */
+    const int32_t* daughter2;    /* [n_cells] index or -1 */
+    const double* time;          /* [n_ctp] MOMAdata::time (already divided by rescale_time) */
+    const double* log_length;    /* [n_ctp] MOMAdata::log_length */
+    const double* fp;            /* [n_ctp] MOMAdata::fp */
+    const int32_t* segment;      /* [n_ctp] MOMAdata::segment, or NULL = all 0 */
+    int32_t noise_model;
+    int32_t division_model;
+    double fp_auto;
+    /* init_cells_f / init_cells_r statistics (moma_input.h:675-735): mean_x0, mean_g0, var_x0, var_g0 of the
+     * first (init_f) and last (init_r) point of all cells with more than one point.  They are population
+     * statistics of the WHOLE data set, so a caller that shards trees over processes computes them once
+     * globally; set compute_init = 1 to have the library derive them from this forest alone. */
+    double init_f[4];
+    double init_r[4];
+    int32_t compute_init;
+    int32_t device;              /* CUDA device ordinal */
+} ggp_forest_desc;
+
+/* first point, in the reference's depth-first order, after which the running sum is NaN (likelihood.h:71) */
+typedef struct {
+    int64_t cell;     /* index into the caller's cell order, -1 if none */
+    int64_t t_index;  /* time index inside that cell */
+} ggp_nan_info;
+
+/* replaces: read_data -> get_segment -> build_cell_genealogy -> init_cells hand-over (main.cpp:385-411) */
+int ggp_forest_create(const ggp_forest_desc* desc, ggp_forest** out);
+void ggp_forest_destroy(ggp_forest* f);
+/* CUDA stream (cudaStream_t) all work of this handle is enqueued on; NULL = the default stream */
+int ggp_forest_set_stream(ggp_forest* f, void* cuda_stream);
+int64_t ggp_forest_n_cells(const ggp_forest* f);
+int64_t ggp_forest_n_ctp(const ggp_forest* f);
+int64_t ggp_forest_n_roots(const ggp_forest* f);
+int ggp_forest_get_init(const ggp_forest* f, double* init_f4, double* init_r4);
+
+/* replaces: total_likelihood(params_vec, cells) (likelihood.h:170-174; objective :125-159) for n_vec
+ * parameter vectors at once (scan main.cpp:105-108, Hessian stencil likelihood.h:211-258, simplex).
+ *   params       [n_vec][11], natural space (the caller applies exp() for log-space search, likelihood.h:161-167)
+ *   root_carry   NULL = every vector is a first ("fresh") evaluation; else in/out [n_roots][16] = the roots'
+ *                persistent MOMAdata::cov (row-major 4x4): vectors are evaluated as if sequentially, each
+ *                root starting from the off-diagonals the previous evaluation left (predictions.h:64-78,
+ *                SURVEY.md H3).  Roots are numbered in cell order.
+ *   out_loglik   [n_vec] +log-likelihood
+ *   out_cell_ll  NULL or [n_vec][n_cells]: each cell's own sum (diagnostics / parity tests)
+ *   nan          NULL or [n_vec]
+ * returns GGP_ERR_NAN if any vector hit a NaN (all vectors are still evaluated). */
+int ggp_loglik(ggp_forest* f, const double* params, int32_t n_vec, double* root_carry,
+               double* out_loglik, double* out_cell_ll, ggp_nan_info* nan);
+
+/* same, but params and out_loglik are DEVICE pointers and nothing is copied or synchronised:
+ * the evaluation is enqueued on the handle's stream (for callers that keep data resident). */
+int ggp_loglik_device(ggp_forest* f, const double* d_params, int32_t n_vec, double* d_out_loglik);
+
+/* replaces: prediction_forward / prediction_backward / combine_predictions (predictions.h:166, 438, 466;
+ * main.cpp:132-140).  params [n_seg][11] indexed by MOMAdata::segment.  Each output is NULL or
+ * [n_ctp][20] = 4 means + the 4x4 covariance row-major, per ctp in the caller's order; the
+ * 14 numbers the reference's writer prints are the mean and the upper triangle (predictions.h:541-552).
+ * Device copies are kept in the handle for ggp_joints. */
+int ggp_predict(ggp_forest* f, const double* params, int32_t n_seg,
+                double* out_forward, double* out_backward, double* out_combined);
+
+/* replaces: collect_joint_distributions (correlation_tree.h:629-648) with a sparse result:
+ * record r = (row_ctp[r], col_ctp[r], rec[r][44]) with 8 means (z_{n+m}, z_n) and the 36 upper-triangular
+ * covariances row-major, in the reference's emission order.  Requires a prior ggp_predict on the handle.
+ * Call with cap = 0 to get the count. */
+int ggp_joints(ggp_forest* f, const double* params, int32_t n_seg, double rel_tol,
+               int64_t cap, int64_t* out_count, int64_t* row_ctp, int64_t* col_ctp, double* rec44);
+
+/* last device kernel time of the handle in milliseconds (CUDA events around the launches of the last call) */
+double ggp_last_kernel_ms(const ggp_forest* f);
+/* number of kernel launches issued by the last call */
+int64_t ggp_last_launch_count(const ggp_forest* f);
+
+const char* ggp_last_error(void);
+const char* ggp_version(void);
+
+/* device self-test of the strict math (exp/log/pow/Dawson/propagate) for callers that hold expected bits:
+ * evaluates fn over n inputs on the device.  fn: 0 exp, 1 log, 2 pow(x, y), 3 dawson.  y may be NULL. */
+int ggp_math_eval(int32_t device, int32_t fn, int64_t n, const double* x, const double* y, double* out);
+/* propagate n independent states (14 doubles each: 4 means + upper triangle) over dt[i] with 7 OU params each
+ * (mean_cov_model, mean_cov_model.h:211); cross (NULL or [n][16]) receives cross_cov_model (:380). */
+int ggp_propagate_eval(int32_t device, int64_t n, const double* state14, const double* dt, const double* p7,
+                       double* out14, double* cross16);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -3,9 +3,9 @@
 // reference build (oracle/_ref) and the host libm.  Test infrastructure; not part of the product.
 #include "../../gfp_gaussian_process_b200/csrc/ggp_tables_data.h"
 #include "../../gfp_gaussian_process_b200/csrc/ggp_dawson.cuh"
-#ifdef GGP_HOSTCHECK_STEP
 #include "../../gfp_gaussian_process_b200/csrc/ggp_step.cuh"
-#endif
+#include "../../gfp_gaussian_process_b200/csrc/ggp_filter.cuh"
+#include "../../gfp_gaussian_process_b200/csrc/ggp_linalg.cuh"
 
 static const GgpMathTables g_tables = GGP_MATH_TABLES_INIT;
 
@@ -14,7 +14,6 @@ void hc_exp(long n, const double* x, double* y) { for (long i = 0; i < n; ++i) y
 void hc_log(long n, const double* x, double* y) { for (long i = 0; i < n; ++i) y[i] = ggp_log(x[i], &g_tables); }
 void hc_pow(long n, const double* x, const double* e, double* y) { for (long i = 0; i < n; ++i) y[i] = ggp_pow(x[i], e[i], &g_tables); }
 void hc_dawson(long n, const double* x, double* y) { for (long i = 0; i < n; ++i) y[i] = ggp_dawson(x[i], &g_tables); }
-#ifdef GGP_HOSTCHECK_STEP
 // state = 4 means + 10 upper-triangular covariances (xx,xg,xl,xq,gg,gl,gq,ll,lq,qq)
 void hc_propagate(long n, const double* state14, const double* dt, const double* p7, double* out14) {
     for (long i = 0; i < n; ++i) {
@@ -27,5 +26,71 @@ void hc_propagate(long n, const double* state14, const double* dt, const double*
         for (int k = 0; k < 10; ++k) out14[14 * i + 4 + k] = s.c[k];
     }
 }
-#endif
+}
+
+// ------------------------------------------------------------------------------------------------
+// whole passes on the host: the product's per-cell bodies (ggp_cell.cuh) and layout (ggp_layout.hpp)
+// driven in the same generation order as the kernels' launch sequence in ggp_b200.cu.
+// ------------------------------------------------------------------------------------------------
+#include "../../gfp_gaussian_process_b200/csrc/ggp_layout.hpp"
+#include "../../gfp_gaussian_process_b200/csrc/ggp_cell.cuh"
+
+static GgpDevForest hc_dev(const GgpLayout& L, const ggp_forest_desc* d) {
+    GgpDevForest F;
+    F.n_cells = L.n_cells; F.n_ctp = L.n_ctp;
+    F.time = d->time; F.x = d->log_length; F.g = d->fp; F.seg = L.seg.data();
+    F.s_off = L.s_off.data(); F.s_n = L.s_n.data(); F.s_parent = L.s_parent.data(); F.s_d1 = L.s_d1.data();
+    F.s_d2 = L.s_d2.data(); F.s_root = L.s_root.data(); F.s_cell = L.s_cell.data(); F.s_dfs0 = L.s_dfs0.data();
+    F.model.noise_scaled = d->noise_model == GGP_NOISE_SCALED;
+    F.model.division_binomial = d->division_model == GGP_DIVISION_BINOMIAL;
+    F.model.fp_auto = d->fp_auto;
+    for (int i = 0; i < 4; ++i) { F.init_f[i] = L.init_f[i]; F.init_r[i] = L.init_r[i]; }
+    return F;
+}
+
+extern "C" {
+
+// returns 0 or -1 (layout error); out_cell_ll [n_vec][n_cells]; carry NULL or [n_roots][16] in/out;
+// nan_rank [n_vec] = depth-first ctp rank of the first NaN term or -1
+int hc_loglik(const ggp_forest_desc* d, const double* params, int n_vec, double* carry, double* out_cell_ll, long long* nan_rank) {
+    GgpLayout L;
+    if (!L.build(d).empty()) return -1;
+    const GgpDevForest F = hc_dev(L, d);
+    std::vector<double> state((size_t)14 * n_vec * L.n_cells);
+    std::vector<unsigned long long> nan(n_vec, ~0ull);
+    GgpFwdArgs A{};
+    A.params = params; A.v0 = 0; A.v_count = n_vec; A.carry = carry; A.state = state.data();
+    A.cell_ll = out_cell_ll; A.nan_key = nan.data();
+    for (int g = 0; g < L.n_gen; ++g)
+        for (int64_t s = L.gen_start[g]; s < L.gen_start[g + 1]; ++s) {
+            if (g == 0 && carry) {
+                double Cc[16];
+                for (int i = 0; i < 16; ++i) Cc[i] = carry[16 * L.s_root[s] + i];
+                for (int v = 0; v < n_vec; ++v) ggp_cell_forward<false, true>(F, A, (int)s, v, params + 11 * v, &g_tables, Cc);
+                for (int i = 0; i < 16; ++i) carry[16 * L.s_root[s] + i] = Cc[i];
+            } else {
+                for (int v = 0; v < n_vec; ++v) ggp_cell_forward<false, false>(F, A, (int)s, v, params + 11 * v, &g_tables, nullptr);
+            }
+        }
+    for (int v = 0; v < n_vec; ++v) nan_rank[v] = nan[v] == ~0ull ? -1 : (long long)nan[v];
+    return 0;
+}
+
+// fwd/bwd/comb [n_ctp][20]; bstate [n_cells][20] in the caller's cell order
+int hc_predict(const ggp_forest_desc* d, const double* params, int n_seg, double* fwd, double* bwd, double* comb, double* bstate_cells) {
+    GgpLayout L;
+    if (!L.build(d).empty() || L.max_seg >= n_seg) return -1;
+    const GgpDevForest F = hc_dev(L, d);
+    std::vector<double> state((size_t)14 * L.n_cells), bstate((size_t)20 * L.n_cells);
+    GgpFwdArgs A{};
+    A.params = params; A.v_count = 1; A.state = state.data(); A.out_fwd = fwd;
+    for (int64_t s = 0; s < L.n_cells; ++s) ggp_cell_forward<true, false>(F, A, (int)s, 0, nullptr, &g_tables, nullptr);
+    GgpBwdArgs B{};
+    B.params = params; B.fwd = fwd; B.bwd = bwd; B.bstate = bstate.data();
+    for (int64_t s = L.n_cells - 1; s >= 0; --s) ggp_cell_backward(F, B, (int)s, &g_tables);
+    for (int64_t i = 0; i < L.n_ctp; ++i) ggp_ctp_combine(fwd + 20 * i, bwd + 20 * i, params + 11 * L.comb_seg[i], comb + 20 * i);
+    for (int64_t s = 0; s < L.n_cells; ++s)
+        for (int k = 0; k < 20; ++k) bstate_cells[20 * (int64_t)L.cell_of_slot[s] + k] = bstate[20 * s + k];
+    return 0;
+}
 }

@@ -65,6 +65,7 @@ SIGNATURES = {
     "ggp_last_error": (C.c_char_p, []),
     "ggp_version": (C.c_char_p, []),
     "ggp_math_eval": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, c_double_p, c_double_p, c_double_p]),
+    "ggp_fp64_peak": (C.c_int, [C.c_int32, c_double_p]),
     "ggp_propagate_eval": (C.c_int, [C.c_int32, C.c_int64, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]),
 }
 

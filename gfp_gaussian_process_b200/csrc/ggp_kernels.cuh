@@ -155,3 +155,15 @@ __global__ void __launch_bounds__(GGP_BLOCK) ggp_propagate_kernel(int64_t n, con
         for (int k = 0; k < 16; ++k) cross16[16 * i + k] = cr[k];
     }
 }
+
+// ---- FP64 pipe peak (roofline denominator; MEASURED_PEAKS.json has no FP64 figure) ----------------
+// register-resident DFMA chains: 8 independent accumulators per thread, 2 flop per DFMA
+__global__ void __launch_bounds__(256) ggp_fp64_peak_kernel(int iters, double a, double b, double* __restrict__ out) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+        x0 = __fma_rn(x0, a, b); x1 = __fma_rn(x1, a, b); x2 = __fma_rn(x2, a, b); x3 = __fma_rn(x3, a, b);
+        x4 = __fma_rn(x4, a, b); x5 = __fma_rn(x5, a, b); x6 = __fma_rn(x6, a, b); x7 = __fma_rn(x7, a, b);
+    }
+    const double r = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (r == 12345.678) out[0] = r;   // never true; keeps the chains alive
+}

@@ -76,6 +76,11 @@ int ggp_forest_set_stream(ggp_forest* f, void* cuda_stream);
 int64_t ggp_forest_n_cells(const ggp_forest* f);
 int64_t ggp_forest_n_ctp(const ggp_forest* f);
 int64_t ggp_forest_n_roots(const ggp_forest* f);
+int64_t ggp_forest_n_generations(const ggp_forest* f);
+/* replace the measurement arrays (MOMAdata::time/log_length/fp, [n_ctp] each, same topology) from host memory;
+ * the copies are asynchronous on the handle's stream when the source is pinned.  Used when the same genealogy
+ * is evaluated on new measurements (and by bench.py's end-to-end leg). */
+int ggp_forest_upload_series(ggp_forest* f, const double* time, const double* log_length, const double* fp);
 int ggp_forest_get_init(const ggp_forest* f, double* init_f4, double* init_r4);
 
 /* replaces: total_likelihood(params_vec, cells) (likelihood.h:170-174; objective :125-159) for n_vec
@@ -111,6 +116,14 @@ int ggp_predict(ggp_forest* f, const double* params, int32_t n_seg,
 int ggp_joints(ggp_forest* f, const double* params, int32_t n_seg, double rel_tol,
                int64_t cap, int64_t* out_count, int64_t* row_ctp, int64_t* col_ctp, double* rec44);
 
+/* waits for the evaluation enqueued by ggp_loglik_device and returns its device time in milliseconds */
+int ggp_sync_kernel_ms(ggp_forest* f, double* ms_out);
+
+/* each cell's MOMAdata::mean/cov as prediction_backward leaves them ([n_cells][20], caller's cell order, 4 means +
+ * 4x4 row-major, in the backward pass's sign-flipped frame); collect_joint_distributions reads them
+ * (correlation_tree.h:519-524).  Requires a prior ggp_predict. */
+int ggp_backward_cell_state(ggp_forest* f, double* out_cell_state20);
+
 /* last device kernel time of the handle in milliseconds (CUDA events around the launches of the last call) */
 double ggp_last_kernel_ms(const ggp_forest* f);
 /* number of kernel launches issued by the last call */
@@ -126,6 +139,10 @@ int ggp_math_eval(int32_t device, int32_t fn, int64_t n, const double* x, const 
  * (mean_cov_model, mean_cov_model.h:211); cross (NULL or [n][16]) receives cross_cov_model (:380). */
 int ggp_propagate_eval(int32_t device, int64_t n, const double* state14, const double* dt, const double* p7,
                        double* out14, double* cross16);
+
+/* measured FP64 FMA throughput of the device in TFLOP/s (register-resident DFMA chains, best of 5): the
+ * roofline denominator of this path, which is bound by the FP64 pipe */
+int ggp_fp64_peak(int32_t device, double* tflops_out);
 
 #ifdef __cplusplus
 }

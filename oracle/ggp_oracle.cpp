@@ -22,7 +22,36 @@
 #include <numeric>
 #include <vector>
 
+#ifdef GGP_ORACLE_USE_REF
+// variant built into oracle/_ref/libggp_oracle_ref.so: the arithmetic core is the REFERENCE'S OWN
+// mean_cov_model.h + Faddeeva.cc (compiled unmodified by ref_shim.cpp); only the Eigen-dependent wrappers
+// below are the restatement.  Used to time the reference's CPU math in bench.py and to cross-check.
+extern "C" {
+void ggp_ref_mean_cov_model(const double*, const double*, double, const double*, double*, double*);
+void ggp_ref_cross_cov_model(const double*, const double*, double, const double*, double*);
+double ggp_ref_dawson(double);
+double ggp_ref_tauint(int, double, double, double, double, double);
+}
+namespace ggp_oracle_math {
+static void mean_cov_model(double* mean, double* cov, double t, const double* p7, bool flip = false) {
+    double q[7] = {flip ? -p7[0] : p7[0], p7[1], p7[2], flip ? -p7[3] : p7[3], p7[4], p7[5], flip ? -p7[6] : p7[6]};
+    double m[4], c[16];
+    ggp_ref_mean_cov_model(mean, cov, t, q, m, c);
+    std::memcpy(mean, m, sizeof m);
+    std::memcpy(cov, c, sizeof c);
+}
+static void cross_cov_model(const double* mean, const double* cov, double t, const double* p7, double* out) {
+    ggp_ref_cross_cov_model(mean, cov, t, p7, out);
+}
+static double dawson(double x) { return ggp_ref_dawson(x); }
+static double I0(double a, double b, double c, double t1, double t0) { return ggp_ref_tauint(0, a, b, c, t1, t0); }
+static double I1(double a, double b, double c, double t1, double t0) { return ggp_ref_tauint(1, a, b, c, t1, t0); }
+static double I2(double a, double b, double c, double t1, double t0) { return ggp_ref_tauint(2, a, b, c, t1, t0); }
+static double I3(double a, double b, double c, double t1, double t0) { return ggp_ref_tauint(3, a, b, c, t1, t0); }
+}  // namespace ggp_oracle_math
+#else
 #include "oracle_math.inc"
+#endif
 
 namespace {
 namespace M = ggp_oracle_math;

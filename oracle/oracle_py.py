@@ -12,6 +12,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(_HERE, "libggp_oracle.so")
 REF_SO = os.path.join(_HERE, "_ref", "libggp_ref.so")
+ORACLE_REF_SO = os.path.join(_HERE, "_ref", "libggp_oracle_ref.so")
 
 dp = C.POINTER(C.c_double)
 lp = C.POINTER(C.c_long)
@@ -29,19 +30,37 @@ def build(force=False):
     """compile the oracle (and, where /root/reference is mounted, the reference shim)."""
     if force or not os.path.exists(ORACLE_SO):
         subprocess.check_call(["make", "-C", _HERE, "libggp_oracle.so"] + (["-B"] if force else []))
-    if os.path.exists("/root/reference/src/mean_cov_model.h") and (force or not os.path.exists(REF_SO)):
-        subprocess.check_call(["make", "-C", _HERE, "_ref/libggp_ref.so"])
+    if os.path.exists("/root/reference/src/mean_cov_model.h") and (force or not os.path.exists(REF_SO) or not os.path.exists(ORACLE_REF_SO)):
+        subprocess.check_call(["make", "-C", _HERE, "_ref/libggp_ref.so", "_ref/libggp_oracle_ref.so"])
 
 
 _oracle = None
 _ref = None
+_use_ref_math = False
+
+
+def use_reference_math(flag=True):
+    """route the oracle's arithmetic core through the reference's own mean_cov_model.h + Faddeeva.cc
+    (oracle/_ref/libggp_oracle_ref.so).  Returns False if that build is not present."""
+    global _oracle, _use_ref_math
+    if flag and not os.path.exists(ORACLE_REF_SO):
+        try:
+            build()
+        except Exception:
+            pass
+        if not os.path.exists(ORACLE_REF_SO):
+            return False
+    if flag != _use_ref_math:
+        _oracle = None
+        _use_ref_math = flag
+    return True
 
 
 def oracle():
     global _oracle
     if _oracle is None:
         build()
-        L = C.CDLL(ORACLE_SO)
+        L = C.CDLL(ORACLE_REF_SO if _use_ref_math else ORACLE_SO)
         L.ggp_oracle_dawson.restype = C.c_double
         L.ggp_oracle_dawson.argtypes = [C.c_double]
         L.ggp_oracle_tauint.restype = C.c_double

@@ -1,0 +1,191 @@
+"""Parity of the CUDA path, called through the C ABI, against the oracle and the committed golden vectors.
+Bars (BASELINE.json north_star): relative 1e-10 on the log-likelihood, 1e-9 on predicted means/covariances.
+What is actually asserted is stronger wherever the arithmetic is order-fixed: bit-for-bit equality of per-cell
+log-likelihood sums, of every stored mean/covariance, of exp/log/pow/Dawson and of the propagation step."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import same_bits, max_rel, example_data, ragged_forest
+from oracle.oracle_py import Oracle
+import gfp_gaussian_process_b200 as ggp
+from gfp_gaussian_process_b200 import api
+
+pytestmark = pytest.mark.gpu
+
+LL_RTOL = 1e-10      # north_star bar for the log-likelihood
+PRED_RTOL = 1e-9     # north_star bar for predicted means / covariances
+
+
+def test_device_math_bits(golden_dir):
+    z = np.load(os.path.join(golden_dir, "libm_bits.npz"))
+    assert same_bits(api.math_eval("exp", z["exp_x"]), z["exp_y"])
+    assert same_bits(api.math_eval("log", z["log_x"]), z["log_y"])
+    assert same_bits(api.math_eval("pow", z["pow_x"], z["pow_e"]), z["pow_y"])
+    g = json.load(open(os.path.join(golden_dir, "dawson_known_answers.json")))
+    xs = np.array([float(e["x"]) for e in g["maple_real"]])
+    ws = np.array([float(e["dawson"]) for e in g["maple_real"]])
+    assert max_rel(api.math_eval("dawson", xs), ws) < 1e-13
+    xs = np.array([float.fromhex(e["x"]) for e in g["mpmath"]])
+    L = __import__("oracle.oracle_py", fromlist=["oracle"]).oracle()
+    assert same_bits(api.math_eval("dawson", xs), np.array([L.ggp_oracle_dawson(v) for v in xs]))
+    rng = np.random.default_rng(0)
+    xs = np.concatenate([rng.uniform(-60, 60, 50000), 10 ** rng.uniform(-12, 9, 5000)])
+    assert same_bits(api.math_eval("dawson", xs), np.array([L.ggp_oracle_dawson(v) for v in xs]))
+
+
+def test_device_step_matches_reference_golden(golden_dir):
+    z = np.load(os.path.join(golden_dir, "ref_step_vectors.npz"))
+    iu = np.triu_indices(4)
+    s14 = np.concatenate([z["mean"], z["cov"].reshape(-1, 4, 4)[:, iu[0], iu[1]]], axis=1)
+    out, cross = api.propagate_eval(s14, z["dt"], z["p7"], cross=True)
+    assert same_bits(out[:, :4], z["mean_out"])
+    assert same_bits(out[:, 4:], z["cov_out"].reshape(-1, 4, 4)[:, iu[0], iu[1]])
+    assert same_bits(cross, z["cross_out"])
+
+
+@pytest.mark.parametrize("noise,division", [("const", "gauss"), ("scaled", "binomial"), ("scaled", "gauss"), ("const", "binomial")])
+def test_loglik_and_predictions_match_oracle(noise, division):
+    P = ggp.PARAMS_CONST_GAUSS if noise == "const" else ggp.PARAMS_SCALED_BINOMIAL
+    d = ggp.simulate_forest(300, 5, params=P, noise_model=noise, division_model=division, seed=5)
+    f = ggp.Forest(d)
+    o = Oracle(d)
+    ll_ref, pc_ref = o.total_loglik(P, per_cell=True)
+    ll, pc = ggp.total_likelihood(P, f, per_cell=True)
+    assert same_bits(pc, pc_ref)                       # every cell's own sum, bit for bit
+    assert abs(ll - ll_ref) <= LL_RTOL * abs(ll_ref)   # the total differs only by summation order
+    assert abs(ll - ll_ref) <= 1e-13 * abs(ll_ref)
+    pr, ref = ggp.prediction_forward_backward(f, [P]), o.predictions([P])
+    for k in ("forward", "backward", "prediction"):
+        for a, b in zip(pr[k], ref[k]):
+            assert max_rel(a, b) <= PRED_RTOL
+            assert same_bits(a, b)
+    bm, bc = api.backward_cell_state(f)
+    assert same_bits(bm, o.cell_mean) and same_bits(bc.reshape(-1, 16), o.cell_cov)
+    f.close()
+
+
+def test_example_dataset_golden(golden_dir):
+    """the reference's own example data (config 1): 1 tree, 77 cells, depth 12, 22 065 points"""
+    data, z = example_data(golden_dir)
+    f = ggp.Forest(data)
+    ll, pc = ggp.total_likelihood(z["params"], f, per_cell=True)
+    assert same_bits(pc, z["cell_ll"])
+    assert abs(ll - float(z["loglik_fresh"])) <= 1e-13 * abs(ll)
+    carry = np.zeros((1, 16))
+    l1 = ggp.total_likelihood(z["params"], f, root_carry=carry)
+    l2 = ggp.total_likelihood(z["params"], f, root_carry=carry)
+    l3 = ggp.total_likelihood(z["params"], f, root_carry=carry)
+    for got, key in ((l1, "loglik_fresh"), (l2, "loglik_second"), (l3, "loglik_third")):
+        assert abs(got - float(z[key])) <= 1e-13 * abs(got)
+    pr = ggp.prediction_forward_backward(f, [z["params"]])
+    for k in ("forward", "backward", "prediction"):
+        assert same_bits(pr[k][0][z["sample"]], z[f"{k}_mean"])
+        assert same_bits(pr[k][1][z["sample"]], z[f"{k}_cov"])
+    f.close()
+
+
+def test_carry_chain_and_batching():
+    """a batch evaluates each vector exactly as a single call would; with root_carry the batch reproduces the
+    reference's sequential history dependence"""
+    P = ggp.PARAMS_SCALED_BINOMIAL
+    d = ggp.simulate_forest(40, 4, noise_model="scaled", division_model="binomial", seed=9)
+    f = ggp.Forest(d)
+    o = Oracle(d)
+    rng = np.random.default_rng(1)
+    vecs = P * (1 + 0.02 * rng.standard_normal((37, 11)))
+    ll_b, pc_b = ggp.total_likelihood(vecs, f, per_cell=True)
+    for i in (0, 5, 36):
+        ll_1, pc_1 = ggp.total_likelihood(vecs[i], f, per_cell=True)
+        assert same_bits(pc_1, pc_b[i]) and ll_1 == ll_b[i]
+        assert same_bits(pc_1, o.total_loglik(vecs[i], per_cell=True)[1])
+    carry = np.zeros((f.n_roots, 16))
+    ll_c, pc_c = ggp.total_likelihood(vecs[:6], f, root_carry=carry, per_cell=True)
+    o.reset()
+    for i in range(6):
+        assert same_bits(pc_c[i], o.total_loglik(vecs[i], fresh=False, per_cell=True)[1])
+    assert same_bits(carry, o.cell_cov[d.roots()])
+    # chaining across two calls equals one chained batch
+    carry2 = np.zeros((f.n_roots, 16))
+    a = ggp.total_likelihood(vecs[:3], f, root_carry=carry2)
+    b = ggp.total_likelihood(vecs[3:6], f, root_carry=carry2)
+    assert np.array_equal(np.concatenate([a, b]), ll_c) and same_bits(carry2, carry)
+    f.close()
+
+
+def test_segments_ragged_and_single_point_cells():
+    d = ragged_forest()
+    P = np.stack([ggp.PARAMS_SCALED_BINOMIAL, ggp.PARAMS_SCALED_BINOMIAL * np.array([1, 1, 1, 2, 1, 1, 1, 1, 1, 1, 1.])])
+    f = ggp.Forest(d)
+    o = Oracle(d)
+    pr, ref = ggp.prediction_forward_backward(f, P), o.predictions(P)
+    for k in ("forward", "backward", "prediction"):
+        assert same_bits(pr[k][0], ref[k][0]) and same_bits(pr[k][1], ref[k][1])
+    assert same_bits(ggp.total_likelihood(P[0], f, per_cell=True)[1], o.total_loglik(P[0], per_cell=True)[1])
+    f.close()
+
+
+def test_nan_is_reported_like_the_reference():
+    d = ggp.simulate_forest(30, 3, seed=2)
+    P = ggp.PARAMS_CONST_GAUSS.copy()
+    P[7] = -1.0
+    f = ggp.Forest(d)
+    o = Oracle(d)
+    assert np.isnan(o.total_loglik(P))
+    with pytest.raises(ggp.LikelihoodNaN) as e:
+        ggp.total_likelihood(P, f)
+    assert (e.value.cell, e.value.t_index) == o.nan
+    good = ggp.total_likelihood(np.stack([ggp.PARAMS_CONST_GAUSS, P]), f, raise_on_nan=False)
+    assert np.isfinite(good[0]) and np.isnan(good[1])
+    f.close()
+
+
+def test_scan_and_hessian_batches_match_oracle():
+    P = ggp.PARAMS_CONST_GAUSS
+    d = ggp.simulate_forest(20, 3, seed=6)
+    f = ggp.Forest(d)
+    o = Oracle(d)
+    samp, ll = ggp.run_bound_1dscan(f, P, 3, 8.0, 12.0, 0.25)
+    assert len(samp) == 16
+    for s, l in zip(samp, ll):
+        q = P.copy()
+        q[3] = s
+        ref = o.total_loglik(q)
+        assert abs(l - ref) <= LL_RTOL * abs(ref)
+    H = ggp.num_hessian_ll(f, P, [0, 3, 7], 1e-3)
+    vecs, hs = api.hessian_stencil(P, [0, 3, 7], 1e-3)
+    ref = np.array([o.total_loglik(v) for v in vecs]).reshape(-1, 4)
+    Href = np.array([(r[0] - r[1] - r[2] + r[3]) / (4 * h1 * h2) for r, (h1, h2) in zip(ref, hs)]).reshape(3, 3)
+    assert np.allclose(H, Href, rtol=1e-6, atol=1e-6 * np.abs(Href).max())
+    f.close()
+
+
+def test_full_size_properties():
+    """BASELINE.json config 2 at full size (10 000 trees x 6 generations, ~12.6 M ctp), checked through size-
+    independent properties: run-to-run determinism, additivity over a split of the trees, and bit-exact per-cell
+    sums against the oracle on a 40-tree sample"""
+    from gfp_gaussian_process_b200 import sharding
+    P = ggp.PARAMS_CONST_GAUSS
+    d = ggp.simulate_forest(10000, 6, seed=20261018)
+    assert d.n_cells == 630000 and 12.0e6 < d.n_ctp < 13.2e6
+    f = ggp.Forest(d)
+    ll, pc = ggp.total_likelihood(P, f, per_cell=True)
+    ll2 = ggp.total_likelihood(P, f)
+    assert np.isfinite(ll) and ll == ll2
+    assert abs(pc.sum() - ll) <= 1e-12 * abs(ll)
+    halves = []
+    for r in range(2):
+        sub, cells, ctp = sharding.shard(d, r, 2)
+        fs = ggp.Forest(sub)
+        l_s, pc_s = ggp.total_likelihood(P, fs, per_cell=True)
+        assert same_bits(pc_s, pc[cells])
+        halves.append(l_s)
+        fs.close()
+    assert abs(sum(halves) - ll) <= 1e-12 * abs(ll)
+    sub, cells, ctp = d.subset(d.roots()[1234:1274])
+    o = Oracle(sub)
+    ll_o, pc_o = o.total_loglik(P, per_cell=True)
+    assert same_bits(pc[cells], pc_o)
+    f.close()

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libggp_b200.so")
+LIB_PATH = os.environ.get("GGP_B200_LIB", os.path.join(_HERE, "libggp_b200.so"))   # override: A/B-testing kernel builds
 
 GGP_OK, GGP_ERR_BAD_ARG, GGP_ERR_NAN, GGP_ERR_CUDA, GGP_ERR_NOMEM = range(5)
 N_PARAMS = 11

@@ -110,6 +110,16 @@ int check_handle(const ggp_forest* f) {
 
 int grid_of(int64_t n) { return (int)((n + GGP_BLOCK - 1) / GGP_BLOCK); }
 
+// the pass kernels use ~100 kB of dynamic shared memory per block (tables + per-thread scratch): opt in once per device
+cudaError_t opt_in_smem() {
+    cudaError_t e = cudaFuncSetAttribute(ggp_forward_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GGP_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ggp_forward_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GGP_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ggp_forward_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GGP_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ggp_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GGP_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ggp_propagate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GGP_SMEM_BYTES);
+    return e;
+}
+
 }  // namespace
 
 extern "C" {
@@ -133,6 +143,7 @@ int ggp_forest_create(const ggp_forest_desc* d, ggp_forest** out) {
         return fail(GGP_ERR_CUDA, e != cudaSuccess ? std::string("no CUDA device: ") + cudaGetErrorString(e) : "no such CUDA device");
     }
     e = cudaSetDevice(d->device);
+    if (e == cudaSuccess) e = opt_in_smem();
     const GgpLayout& L = f->L;
     f->device = d->device;
     f->n_cells = L.n_cells;
@@ -264,9 +275,9 @@ int enqueue_loglik(ggp_forest* f, const double* d_params, int32_t n_vec, double*
             A.out_fwd = nullptr;
             const int gx = grid_of(A.n_slots);
             if (g == 0 && d_carry)
-                ggp_forward_kernel<false, true><<<dim3(gx, 1), GGP_BLOCK, 0, f->stream>>>(F, A);
+                ggp_forward_kernel<false, true><<<dim3(gx, 1), GGP_BLOCK, GGP_SMEM_BYTES, f->stream>>>(F, A);
             else
-                ggp_forward_kernel<false, false><<<dim3(gx, vc), GGP_BLOCK, 0, f->stream>>>(F, A);
+                ggp_forward_kernel<false, false><<<dim3(gx, vc), GGP_BLOCK, GGP_SMEM_BYTES, f->stream>>>(F, A);
             ++f->last_launches;
         }
         ggp_reduce_kernel<<<vc, 256, 0, f->stream>>>(f->w_partial.p, n_partial, d_out + v0);
@@ -379,7 +390,7 @@ int ggp_predict(ggp_forest* f, const double* params, int32_t n_seg, double* out_
         A.v_count = 1;
         A.state = f->w_state.p;
         A.out_fwd = f->fwd.p;
-        ggp_forward_kernel<true, false><<<dim3(grid_of(A.n_slots), 1), GGP_BLOCK, 0, s>>>(F, A);
+        ggp_forward_kernel<true, false><<<dim3(grid_of(A.n_slots), 1), GGP_BLOCK, GGP_SMEM_BYTES, s>>>(F, A);
         ++f->last_launches;
     }
     for (int g = f->n_gen - 1; g >= 0; --g) {
@@ -390,7 +401,7 @@ int ggp_predict(ggp_forest* f, const double* params, int32_t n_seg, double* out_
         B.fwd = f->fwd.p;
         B.bwd = f->bwd.p;
         B.bstate = f->bstate.p;
-        ggp_backward_kernel<<<grid_of(B.n_slots), GGP_BLOCK, 0, s>>>(F, B);
+        ggp_backward_kernel<<<grid_of(B.n_slots), GGP_BLOCK, GGP_SMEM_BYTES, s>>>(F, B);
         ++f->last_launches;
     }
     ggp_combine_kernel<<<grid_of(M), GGP_BLOCK, 0, s>>>(M, f->fwd.p, f->bwd.p, f->comb_seg.p, f->pred_params.p, f->comb.p);
@@ -431,7 +442,7 @@ int ggp_math_eval(int32_t device, int32_t fn, int64_t n, const double* x, const 
     GGP_CUDA(dout.ensure(n));
     GGP_CUDA(cudaMemcpy(dx.p, x, n * sizeof(double), cudaMemcpyHostToDevice));
     if (y) GGP_CUDA(cudaMemcpy(dy.p, y, n * sizeof(double), cudaMemcpyHostToDevice));
-    ggp_math_kernel<<<grid_of(n), GGP_BLOCK>>>(fn, n, dx.p, dy.p, dout.p);
+    ggp_math_kernel<<<grid_of(n), GGP_BLOCK, sizeof(GgpMathTables)>>>(fn, n, dx.p, dy.p, dout.p);
     cudaError_t e = cudaDeviceSynchronize();
     if (e == cudaSuccess) e = cudaMemcpy(out, dout.p, n * sizeof(double), cudaMemcpyDeviceToHost);
     dx.release(); dy.release(); dout.release();
@@ -452,7 +463,8 @@ int ggp_propagate_eval(int32_t device, int64_t n, const double* state14, const d
     GGP_CUDA(cudaMemcpy(ds.p, state14, 14 * n * sizeof(double), cudaMemcpyHostToDevice));
     GGP_CUDA(cudaMemcpy(dd.p, dt, n * sizeof(double), cudaMemcpyHostToDevice));
     GGP_CUDA(cudaMemcpy(dp.p, p7, 7 * n * sizeof(double), cudaMemcpyHostToDevice));
-    ggp_propagate_kernel<<<grid_of(n), GGP_BLOCK>>>(n, ds.p, dd.p, dp.p, dout.p, cross16 ? dc.p : nullptr);
+    GGP_CUDA(opt_in_smem());
+    ggp_propagate_kernel<<<grid_of(n), GGP_BLOCK, GGP_SMEM_BYTES>>>(n, ds.p, dd.p, dp.p, dout.p, cross16 ? dc.p : nullptr);
     cudaError_t e = cudaDeviceSynchronize();
     if (e == cudaSuccess) e = cudaMemcpy(out14, dout.p, 14 * n * sizeof(double), cudaMemcpyDeviceToHost);
     if (e == cudaSuccess && cross16) e = cudaMemcpy(cross16, dc.p, 16 * n * sizeof(double), cudaMemcpyDeviceToHost);

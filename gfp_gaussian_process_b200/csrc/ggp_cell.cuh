@@ -98,7 +98,7 @@ GGP_HD void ggp_store20(double* __restrict__ dst, const double* __restrict__ mea
 template <bool PRED, bool CHAIN>
 GGP_HD double ggp_cell_forward(const GgpDevForest& F, const GgpFwdArgs& A, int slot, int v,
                                const double* __restrict__ p_lik, const GgpMathTables* __restrict__ T,
-                               double* __restrict__ Cc) {
+                               const GgpScratch& S, double* __restrict__ Cc) {
     const int64_t off = F.s_off[slot];
     const int n = F.s_n[slot];
     const int parent = F.s_parent[slot];
@@ -144,7 +144,7 @@ GGP_HD double ggp_cell_forward(const GgpDevForest& F, const GgpFwdArgs& A, int s
     while (t + 1 < n) {
         const double* pp = PRED ? A.params + GGP_NP * F.seg[from] : p_lik;
         const double dt = F.time[off + t + 1] - F.time[from];
-        ggp_propagate(s, dt, ggp_ou(pp, false), T);
+        ggp_propagate(s, dt, ggp_ou(pp, false), T, S);
         if (t < 0) ggp_divide(s, pp[9], pp[10], F.model);
         ++t;
         from = off + t;
@@ -176,7 +176,8 @@ GGP_HD double ggp_cell_forward(const GgpDevForest& F, const GgpFwdArgs& A, int s
 // ------------------------------------------------------------------------------------------------
 // backward filter of one cell (predictions.h:368-422), cells processed from the leaves upward
 // ------------------------------------------------------------------------------------------------
-GGP_HD void ggp_cell_backward(const GgpDevForest& F, const GgpBwdArgs& A, int slot, const GgpMathTables* __restrict__ T) {
+GGP_HD void ggp_cell_backward(const GgpDevForest& F, const GgpBwdArgs& A, int slot, const GgpMathTables* __restrict__ T,
+                              const GgpScratch& S) {
     const int64_t off = F.s_off[slot];
     const int n = F.s_n[slot];
     const int d1 = F.s_d1[slot], d2 = F.s_d2[slot];
@@ -229,7 +230,7 @@ GGP_HD void ggp_cell_backward(const GgpDevForest& F, const GgpBwdArgs& A, int sl
     while (t > 0) {
         const double* pp = A.params + GGP_NP * F.seg[off + t - 1];
         const double dt = F.time[from] - F.time[off + t - 1];
-        ggp_propagate(s, dt, ggp_ou(pp, true), T);
+        ggp_propagate(s, dt, ggp_ou(pp, true), T, S);
         --t;
         from = off + t;
         ggp_state_to16(s, C);

@@ -48,3 +48,38 @@ GGP_HD_NOINLINE double ggp_dawson(double x, const GgpMathTables* __restrict__ M)
     double w = (x >= 0) ? ggp_w_im_pos(x, M->dawson_tab) : -ggp_w_im_pos(-x, M->dawson_tab);
     return spi2 * w;
 }
+
+// N independent Dawson values with the common path (Chebyshev piece, 0.0309 < |x| <= 45) as straight-line
+// code; the rare branches go through the full routine.  Same operations, same bits as ggp_dawson.
+template <int N>
+GGP_HD void ggp_dawson_n(const double* __restrict__ x, double* __restrict__ y, const GgpMathTables* __restrict__ M) {
+    const double spi2 = 0.8862269254527580136490837416705725913990;
+    bool slow = false;
+    double ax[N], y100[N];
+    int idx[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        ax[i] = fabs(x[i]);
+        y100[i] = 100 / (1 + ax[i]);
+        const int pc = (int)y100[i];
+        const bool ok = (ax[i] <= 45.0) && (pc < 97);   // false for NaN as well
+        slow = slow || !ok;
+        idx[i] = ok ? pc : 0;
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const double t = 2 * y100[i] - (double)(2 * idx[i] + 1);
+        const double* __restrict__ c = M->dawson_tab + 9 * idx[i];
+        double p = GGP_LDG(c + 8);
+#pragma unroll
+        for (int k = 7; k >= 0; --k) p = GGP_LDG(c + k) + p * t;
+        y[i] = spi2 * ((x[i] >= 0) ? p : -p);
+    }
+    if (slow) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const int pc = (int)y100[i];
+            if (!((ax[i] <= 45.0) && (pc < 97))) y[i] = ggp_dawson(x[i], M);
+        }
+    }
+}

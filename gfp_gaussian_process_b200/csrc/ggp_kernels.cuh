@@ -20,6 +20,17 @@
 
 __device__ const GgpMathTables g_ggp_tables = GGP_MATH_TABLES_INIT;
 
+// dynamic shared memory of the pass kernels: [math tables][per-thread scratch, GGP_SCRATCH x GGP_BLOCK doubles]
+#define GGP_SMEM_BYTES (sizeof(GgpMathTables) + (size_t)GGP_SCRATCH * GGP_BLOCK * sizeof(double))
+extern __shared__ __align__(16) unsigned char ggp_smem[];
+
+__device__ __forceinline__ GgpScratch ggp_thread_scratch() {
+    GgpScratch S;
+    S.base = reinterpret_cast<double*>(ggp_smem + sizeof(GgpMathTables)) + threadIdx.x;
+    S.stride = GGP_BLOCK;
+    return S;
+}
+
 __device__ __forceinline__ void ggp_stage_tables(GgpMathTables* sm) {
     const uint64_t* src = reinterpret_cast<const uint64_t*>(&g_ggp_tables);
     uint64_t* dst = reinterpret_cast<uint64_t*>(sm);
@@ -44,10 +55,11 @@ __device__ __forceinline__ double ggp_block_sum(double v, double* red) {
 
 template <bool PRED, bool CHAIN>
 __global__ void __launch_bounds__(GGP_BLOCK) ggp_forward_kernel(const GgpDevForest F, const GgpFwdArgs A) {
-    __shared__ GgpMathTables T;
+    GgpMathTables& T = *reinterpret_cast<GgpMathTables*>(ggp_smem);
     __shared__ double sp[GGP_NP];
     __shared__ double red[GGP_BLOCK / 32];
     ggp_stage_tables(&T);
+    const GgpScratch S = ggp_thread_scratch();
 
     const int lane_slot = blockIdx.x * GGP_BLOCK + threadIdx.x;
     const bool active = lane_slot < A.n_slots;
@@ -67,7 +79,7 @@ __global__ void __launch_bounds__(GGP_BLOCK) ggp_forward_kernel(const GgpDevFore
             __syncthreads();
         }
         double own = 0.0;
-        if (active) own = ggp_cell_forward<PRED, CHAIN>(F, A, slot, v, sp, &T, Cc);
+        if (active) own = ggp_cell_forward<PRED, CHAIN>(F, A, slot, v, sp, &T, S, Cc);
         if (!PRED) {
             const double bs = ggp_block_sum(own, red);
             if (threadIdx.x == 0) A.partial[(int64_t)v * A.n_partial + A.partial0 + blockIdx.x] = bs;
@@ -96,11 +108,11 @@ __global__ void __launch_bounds__(256) ggp_reduce_kernel(const double* __restric
 }
 
 __global__ void __launch_bounds__(GGP_BLOCK) ggp_backward_kernel(const GgpDevForest F, const GgpBwdArgs A) {
-    __shared__ GgpMathTables T;
+    GgpMathTables& T = *reinterpret_cast<GgpMathTables*>(ggp_smem);
     ggp_stage_tables(&T);
     const int lane_slot = blockIdx.x * GGP_BLOCK + threadIdx.x;
     if (lane_slot >= A.n_slots) return;
-    ggp_cell_backward(F, A, A.slot0 + lane_slot, &T);
+    ggp_cell_backward(F, A, A.slot0 + lane_slot, &T, ggp_thread_scratch());
 }
 
 __global__ void __launch_bounds__(GGP_BLOCK) ggp_combine_kernel(int64_t n_ctp, const double* __restrict__ fwd,
@@ -116,7 +128,7 @@ __global__ void __launch_bounds__(GGP_BLOCK) ggp_combine_kernel(int64_t n_ctp, c
 // ---- self-test kernels (ggp_math_eval / ggp_propagate_eval) -------------------------------------
 __global__ void __launch_bounds__(GGP_BLOCK) ggp_math_kernel(int fn, int64_t n, const double* __restrict__ x,
                                                              const double* __restrict__ y, double* __restrict__ out) {
-    __shared__ GgpMathTables T;
+    GgpMathTables& T = *reinterpret_cast<GgpMathTables*>(ggp_smem);
     ggp_stage_tables(&T);
     const int64_t i = (int64_t)blockIdx.x * GGP_BLOCK + threadIdx.x;
     if (i >= n) return;
@@ -134,7 +146,7 @@ __global__ void __launch_bounds__(GGP_BLOCK) ggp_propagate_kernel(int64_t n, con
                                                                   const double* __restrict__ dt,
                                                                   const double* __restrict__ p7, double* __restrict__ out14,
                                                                   double* __restrict__ cross16) {
-    __shared__ GgpMathTables T;
+    GgpMathTables& T = *reinterpret_cast<GgpMathTables*>(ggp_smem);
     ggp_stage_tables(&T);
     const int64_t i = (int64_t)blockIdx.x * GGP_BLOCK + threadIdx.x;
     if (i >= n) return;
@@ -145,7 +157,7 @@ __global__ void __launch_bounds__(GGP_BLOCK) ggp_propagate_kernel(int64_t n, con
     for (int k = 0; k < 10; ++k) s.c[k] = state14[14 * i + 4 + k];
     GgpOuParams p = {p7[7 * i], p7[7 * i + 1], p7[7 * i + 2], p7[7 * i + 3], p7[7 * i + 4], p7[7 * i + 5], p7[7 * i + 6]};
     double cr[16];
-    ggp_propagate_impl(s, dt[i], p, &T, cross16 ? cr : nullptr);
+    ggp_propagate_impl(s, dt[i], p, &T, ggp_thread_scratch(), cross16 ? cr : nullptr);
 #pragma unroll
     for (int k = 0; k < 4; ++k) out14[14 * i + k] = s.m[k];
 #pragma unroll

@@ -21,7 +21,9 @@ void hc_propagate(long n, const double* state14, const double* dt, const double*
         for (int k = 0; k < 4; ++k) s.m[k] = state14[14 * i + k];
         for (int k = 0; k < 10; ++k) s.c[k] = state14[14 * i + 4 + k];
         GgpOuParams p = {p7[0], p7[1], p7[2], p7[3], p7[4], p7[5], p7[6]};
-        ggp_propagate(s, dt[i], p, &g_tables);
+        double scratch[GGP_SCRATCH];
+        GgpScratch S{scratch, 1};
+        ggp_propagate(s, dt[i], p, &g_tables, S);
         for (int k = 0; k < 4; ++k) out14[14 * i + k] = s.m[k];
         for (int k = 0; k < 10; ++k) out14[14 * i + 4 + k] = s.c[k];
     }
@@ -55,6 +57,8 @@ extern "C" {
 int hc_loglik(const ggp_forest_desc* d, const double* params, int n_vec, double* carry, double* out_cell_ll, long long* nan_rank) {
     GgpLayout L;
     if (!L.build(d).empty()) return -1;
+    double scratch[GGP_SCRATCH];
+    const GgpScratch S{scratch, 1};
     const GgpDevForest F = hc_dev(L, d);
     std::vector<double> state((size_t)14 * n_vec * L.n_cells);
     std::vector<unsigned long long> nan(n_vec, ~0ull);
@@ -66,10 +70,10 @@ int hc_loglik(const ggp_forest_desc* d, const double* params, int n_vec, double*
             if (g == 0 && carry) {
                 double Cc[16];
                 for (int i = 0; i < 16; ++i) Cc[i] = carry[16 * L.s_root[s] + i];
-                for (int v = 0; v < n_vec; ++v) ggp_cell_forward<false, true>(F, A, (int)s, v, params + 11 * v, &g_tables, Cc);
+                for (int v = 0; v < n_vec; ++v) ggp_cell_forward<false, true>(F, A, (int)s, v, params + 11 * v, &g_tables, S, Cc);
                 for (int i = 0; i < 16; ++i) carry[16 * L.s_root[s] + i] = Cc[i];
             } else {
-                for (int v = 0; v < n_vec; ++v) ggp_cell_forward<false, false>(F, A, (int)s, v, params + 11 * v, &g_tables, nullptr);
+                for (int v = 0; v < n_vec; ++v) ggp_cell_forward<false, false>(F, A, (int)s, v, params + 11 * v, &g_tables, S, nullptr);
             }
         }
     for (int v = 0; v < n_vec; ++v) nan_rank[v] = nan[v] == ~0ull ? -1 : (long long)nan[v];
@@ -80,14 +84,16 @@ int hc_loglik(const ggp_forest_desc* d, const double* params, int n_vec, double*
 int hc_predict(const ggp_forest_desc* d, const double* params, int n_seg, double* fwd, double* bwd, double* comb, double* bstate_cells) {
     GgpLayout L;
     if (!L.build(d).empty() || L.max_seg >= n_seg) return -1;
+    double scratch[GGP_SCRATCH];
+    const GgpScratch S{scratch, 1};
     const GgpDevForest F = hc_dev(L, d);
     std::vector<double> state((size_t)14 * L.n_cells), bstate((size_t)20 * L.n_cells);
     GgpFwdArgs A{};
     A.params = params; A.v_count = 1; A.state = state.data(); A.out_fwd = fwd;
-    for (int64_t s = 0; s < L.n_cells; ++s) ggp_cell_forward<true, false>(F, A, (int)s, 0, nullptr, &g_tables, nullptr);
+    for (int64_t s = 0; s < L.n_cells; ++s) ggp_cell_forward<true, false>(F, A, (int)s, 0, nullptr, &g_tables, S, nullptr);
     GgpBwdArgs B{};
     B.params = params; B.fwd = fwd; B.bwd = bwd; B.bstate = bstate.data();
-    for (int64_t s = L.n_cells - 1; s >= 0; --s) ggp_cell_backward(F, B, (int)s, &g_tables);
+    for (int64_t s = L.n_cells - 1; s >= 0; --s) ggp_cell_backward(F, B, (int)s, &g_tables, S);
     for (int64_t i = 0; i < L.n_ctp; ++i) ggp_ctp_combine(fwd + 20 * i, bwd + 20 * i, params + 11 * L.comb_seg[i], comb + 20 * i);
     for (int64_t s = 0; s < L.n_cells; ++s)
         for (int k = 0; k < 20; ++k) bstate_cells[20 * (int64_t)L.cell_of_slot[s] + k] = bstate[20 * s + k];

@@ -139,7 +139,7 @@ def backward_cell_state(forest: Forest):
 def math_eval(fn, x, y=None, device=0):
     """device self-test of the strict exp/log/pow/dawson (ggp_math_eval)."""
     lib = _lib.load()
-    code = {"exp": 0, "log": 1, "pow": 2, "dawson": 3}[fn]
+    code = {"exp": 0, "log": 1, "pow": 2, "dawson": 3, "div": 4}[fn]
     x = np.ascontiguousarray(x, dtype=np.float64)
     out = np.empty_like(x)
     yp = None

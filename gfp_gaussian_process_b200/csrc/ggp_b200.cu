@@ -434,7 +434,7 @@ int ggp_backward_cell_state(ggp_forest* f, double* out_cell_state20) {
 }
 
 int ggp_math_eval(int32_t device, int32_t fn, int64_t n, const double* x, const double* y, double* out) {
-    if (!x || !out || n <= 0 || fn < 0 || fn > 3 || (fn == 2 && !y)) return fail(GGP_ERR_BAD_ARG, "bad argument");
+    if (!x || !out || n <= 0 || fn < 0 || fn > 4 || (fn >= 2 && fn != 3 && !y)) return fail(GGP_ERR_BAD_ARG, "bad argument");
     GGP_CUDA(cudaSetDevice(device));
     DevBuf<double> dx, dy, dout;
     GGP_CUDA(dx.ensure(n));

@@ -137,7 +137,8 @@ __global__ void __launch_bounds__(GGP_BLOCK) ggp_math_kernel(int fn, int64_t n, 
         case 0: r = ggp_exp(x[i], &T); break;
         case 1: r = ggp_log(x[i], &T); break;
         case 2: r = ggp_pow(x[i], y[i], &T); break;
-        default: r = ggp_dawson(x[i], &T); break;
+        case 3: r = ggp_dawson(x[i], &T); break;
+        default: r = x[i] / ggp_divisor(y[i]); break;
     }
     out[i] = r;
 }

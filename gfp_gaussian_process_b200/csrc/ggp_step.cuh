@@ -87,8 +87,9 @@ static const GgpGroup ggp_group_host[17] = GGP_GROUP_INIT;
 #endif
 
 struct GgpStepCommon {
-    double a, sqa, twoa, two_sqa, m2sqa, p2sqa, foura;
-    double den0, den1, den2, den3;   // 2 sqrt a, 4 a^1.5, 8 a^2.5, 16 a^3.5
+    double a, sqa, twoa, m2sqa, p2sqa;
+    GgpDivisor two_sqa, foura;
+    GgpDivisor den0, den1, den2, den3;   // 2 sqrt a, 4 a^1.5, 8 a^2.5, 16 a^3.5
     double foura2;                   // 4 a^2
     double t, t2, at2, a4t2;
 };
@@ -179,15 +180,15 @@ GGP_HD void ggp_propagate_impl(GgpState& s, double t, const GgpOuParams& p, cons
     k.a = Cll / 2.;
     k.sqa = GGP_SQRT(k.a);
     k.twoa = 2. * k.a;
-    k.two_sqa = 2. * k.sqa;
+    k.two_sqa = ggp_divisor(2. * k.sqa);
     k.m2sqa = -2. * k.sqa;
     k.p2sqa = 2. * k.sqa;
-    k.foura = 4. * k.a;
+    k.foura = ggp_divisor(4. * k.a);
     k.foura2 = 4 * (k.a * k.a);
-    k.den0 = 2. * k.sqa;
-    k.den1 = 4. * ggp_pow(k.a, 1.5, M);
-    k.den2 = 8. * ggp_pow(k.a, 2.5, M);
-    k.den3 = 16. * ggp_pow(k.a, 3.5, M);
+    k.den0 = k.two_sqa;
+    k.den1 = ggp_divisor(4. * ggp_pow(k.a, 1.5, M));
+    k.den2 = ggp_divisor(8. * ggp_pow(k.a, 2.5, M));
+    k.den3 = ggp_divisor(16. * ggp_pow(k.a, 3.5, M));
     k.t = t;
     k.t2 = 2 * t;
     k.at2 = k.a * (t * t);
@@ -249,6 +250,10 @@ GGP_HD void ggp_propagate_impl(GgpState& s, double t, const GgpOuParams& p, cons
     const double ebgq = S[GGP_S_G + 18];   // exp((b+gq) t)
     const double e2bt = S[GGP_S_G + 19];   // exp(2 b t)
     const double omegl = 1 - egl;
+    // divisors met more than once (see GgpDivisor): the reciprocal refinement is shared, the quotients are IEEE
+    const GgpDivisor gl_ = ggp_divisor(gl), gq_ = ggp_divisor(gq), ebt_ = ggp_divisor(ebt), ebgl_ = ggp_divisor(ebgl),
+                     ebgq_ = ggp_divisor(ebgq), ebt_gl_ = ggp_divisor(ebt * gl), ebgl_gl_ = ggp_divisor(ebgl * gl),
+                     two_gq_ = ggp_divisor(2. * gq), two_gq2_ = ggp_divisor(2. * (gq * gq));
 
     // ---- segment A: the (., c1) and (., c1 - gl t) groups over [0, t] ----
     ggp_eval_groups(S, 0, 4, k, M);
@@ -258,29 +263,29 @@ GGP_HD void ggp_propagate_impl(GgpState& s, double t, const GgpOuParams& p, cons
     const GgpInts<2> jBm_c1l = ggp_load_ints<2>(S, 7);
 
     // new mean (mean_cov_model.h:73-87); needed by the covariance terms below
-    double nm0 = bx + ml * t + (bl - ml) * omegl / gl;
-    double nm1 = bg / ebt + Clq * jBm_c1.I[1] + mq * jB_c1.I[0] + (bq + Cxq - mq) * jBm_c1.I[0];
+    double nm0 = bx + ml * t + (bl - ml) * omegl / gl_;
+    double nm1 = bg / ebt_ + Clq * jBm_c1.I[1] + mq * jB_c1.I[0] + (bq + Cxq - mq) * jBm_c1.I[0];
     double nm2 = ml + (bl - ml) * egl;
     double nm3 = mq + (bq - mq) * egq;
 
     if (cross) {   // mean_cov_model.h:282-377: uses only the two (., c1) groups over [0, t]
-        cross[0] = Cxx + Cxl * omegl / gl;
-        cross[1] = Cxg + Cgl * omegl / gl;
-        cross[2] = Cxl + Cll * omegl / gl;
-        cross[3] = Cxq + Clq * omegl / gl;
-        cross[4] = (bg * bx) / ebt + Cxg / ebt + Cxl * mq * jB_c1.I[1]
+        cross[0] = Cxx + Cxl * omegl / gl_;
+        cross[1] = Cxg + Cgl * omegl / gl_;
+        cross[2] = Cxl + Cll * omegl / gl_;
+        cross[3] = Cxq + Clq * omegl / gl_;
+        cross[4] = (bg * bx) / ebt_ + Cxg / ebt_ + Cxl * mq * jB_c1.I[1]
                    + (bx * Clq + bq * Cxl + Cxl * Cxq + Clq * Cxx - Cxl * mq) * jBm_c1.I[1]
                    + Clq * Cxl * jBm_c1.I[2] + (bx * mq + Cxx * mq) * jB_c1.I[0]
                    + (bq * bx + Cxq + bx * Cxq + bq * Cxx + Cxq * Cxx - bx * mq - Cxx * mq) * jBm_c1.I[0] - nm1 * bx;
-        cross[5] = (bg * bg) / ebt + Cgg / ebt + Cgl * mq * jB_c1.I[1]
+        cross[5] = (bg * bg) / ebt_ + Cgg / ebt_ + Cgl * mq * jB_c1.I[1]
                    + (bq * Cgl + bg * Clq + Clq * Cxg + Cgl * Cxq - Cgl * mq) * jBm_c1.I[1]
                    + Cgl * Clq * jBm_c1.I[2] + (bg * mq + Cxg * mq) * jB_c1.I[0]
                    + (bg * bq + Cgq + bq * Cxg + bg * Cxq + Cxg * Cxq - bg * mq - Cxg * mq) * jBm_c1.I[0] - nm1 * bg;
-        cross[6] = (bg * bl) / ebt + Cgl / ebt + Cll * mq * jB_c1.I[1]
+        cross[6] = (bg * bl) / ebt_ + Cgl / ebt_ + Cll * mq * jB_c1.I[1]
                    + (bq * Cll + bl * Clq + Clq * Cxl + Cll * Cxq - Cll * mq) * jBm_c1.I[1]
                    + Cll * Clq * jBm_c1.I[2] + (bl * mq + Cxl * mq) * jB_c1.I[0]
                    + (bl * bq + Clq + bq * Cxl + bl * Cxq + Cxl * Cxq - bl * mq - Cxl * mq) * jBm_c1.I[0] - nm1 * bl;
-        cross[7] = (bg * bq) / ebt + Cgq / ebt + Clq * mq * jB_c1.I[1]
+        cross[7] = (bg * bq) / ebt_ + Cgq / ebt_ + Clq * mq * jB_c1.I[1]
                    + (2 * bq * Clq + 2 * Clq * Cxq - Clq * mq) * jBm_c1.I[1]
                    + (Clq * Clq) * jBm_c1.I[2] + (bq * mq + Cxq * mq) * jB_c1.I[0]
                    + ((bq * bq) + Cqq + 2 * bq * Cxq + (Cxq * Cxq) - bq * mq - Cxq * mq) * jBm_c1.I[0] - nm1 * bq;
@@ -290,28 +295,28 @@ GGP_HD void ggp_propagate_impl(GgpState& s, double t, const GgpOuParams& p, cons
 
     // ---- cov_xg, mean_cov_model.h:97-115 ----
     double n_xg =
-        (bg * bx) / ebt + Cxg / ebt + (bg * bl) / (ebt * gl) + Cgl / (ebt * gl) - (bg * bl) / (ebgl * gl)
-        - Cgl / (ebgl * gl) - (bg * ml) / (ebt * gl) + (bg * ml) / (ebgl * gl) + (bg * ml * t) / ebt
-        + (Cxl * mq + (Cll * mq) / gl) * jB_c1.I[1]
-        - (Cll * mq * jB_c1l.I[1]) / gl
-        + (bx * Clq + bq * Cxl + Cxl * Cxq + Clq * Cxx + (bq * Cll) / gl + (bl * Clq) / gl + (Clq * Cxl) / gl
-           + (Cll * Cxq) / gl - (Clq * ml) / gl - Cxl * mq - (Cll * mq) / gl + Clq * ml * t) * jBm_c1.I[1]
-        + (-((bq * Cll) / gl) - (bl * Clq) / gl - (Clq * Cxl) / gl - (Cll * Cxq) / gl + (Clq * ml) / gl
-           + (Cll * mq) / gl) * jBm_c1l.I[1]
-        + (Clq * Cxl + (Cll * Clq) / gl) * jBm_c1.I[2]
-        - (Cll * Clq * jBm_c1l.I[2]) / gl
-        + (bx * mq + Cxx * mq + (bl * mq) / gl + (Cxl * mq) / gl - (ml * mq) / gl + ml * mq * t) * jB_c1.I[0]
-        + (-((bl * mq) / gl) - (Cxl * mq) / gl + (ml * mq) / gl) * jB_c1l.I[0]
-        + (bq * bx + Cxq + bx * Cxq + bq * Cxx + Cxq * Cxx + (bl * bq) / gl + Clq / gl + (bq * Cxl) / gl
-           + (bl * Cxq) / gl + (Cxl * Cxq) / gl - (bq * ml) / gl - (Cxq * ml) / gl - bx * mq - Cxx * mq
-           - (bl * mq) / gl - (Cxl * mq) / gl + (ml * mq) / gl + bq * ml * t + Cxq * ml * t - ml * mq * t) * jBm_c1.I[0]
-        + (-((bl * bq) / gl) - Clq / gl - (bq * Cxl) / gl - (bl * Cxq) / gl - (Cxl * Cxq) / gl + (bq * ml) / gl
-           + (Cxq * ml) / gl + (bl * mq) / gl + (Cxl * mq) / gl - (ml * mq) / gl) * jBm_c1l.I[0]
+        (bg * bx) / ebt_ + Cxg / ebt_ + (bg * bl) / ebt_gl_ + Cgl / ebt_gl_ - (bg * bl) / ebgl_gl_
+        - Cgl / ebgl_gl_ - (bg * ml) / ebt_gl_ + (bg * ml) / ebgl_gl_ + (bg * ml * t) / ebt_
+        + (Cxl * mq + (Cll * mq) / gl_) * jB_c1.I[1]
+        - (Cll * mq * jB_c1l.I[1]) / gl_
+        + (bx * Clq + bq * Cxl + Cxl * Cxq + Clq * Cxx + (bq * Cll) / gl_ + (bl * Clq) / gl_ + (Clq * Cxl) / gl_
+           + (Cll * Cxq) / gl_ - (Clq * ml) / gl_ - Cxl * mq - (Cll * mq) / gl_ + Clq * ml * t) * jBm_c1.I[1]
+        + (-((bq * Cll) / gl_) - (bl * Clq) / gl_ - (Clq * Cxl) / gl_ - (Cll * Cxq) / gl_ + (Clq * ml) / gl_
+           + (Cll * mq) / gl_) * jBm_c1l.I[1]
+        + (Clq * Cxl + (Cll * Clq) / gl_) * jBm_c1.I[2]
+        - (Cll * Clq * jBm_c1l.I[2]) / gl_
+        + (bx * mq + Cxx * mq + (bl * mq) / gl_ + (Cxl * mq) / gl_ - (ml * mq) / gl_ + ml * mq * t) * jB_c1.I[0]
+        + (-((bl * mq) / gl_) - (Cxl * mq) / gl_ + (ml * mq) / gl_) * jB_c1l.I[0]
+        + (bq * bx + Cxq + bx * Cxq + bq * Cxx + Cxq * Cxx + (bl * bq) / gl_ + Clq / gl_ + (bq * Cxl) / gl_
+           + (bl * Cxq) / gl_ + (Cxl * Cxq) / gl_ - (bq * ml) / gl_ - (Cxq * ml) / gl_ - bx * mq - Cxx * mq
+           - (bl * mq) / gl_ - (Cxl * mq) / gl_ + (ml * mq) / gl_ + bq * ml * t + Cxq * ml * t - ml * mq * t) * jBm_c1.I[0]
+        + (-((bl * bq) / gl_) - Clq / gl_ - (bq * Cxl) / gl_ - (bl * Cxq) / gl_ - (Cxl * Cxq) / gl_ + (bq * ml) / gl_
+           + (Cxq * ml) / gl_ + (bl * mq) / gl_ + (Cxl * mq) / gl_ - (ml * mq) / gl_) * jBm_c1l.I[0]
         - nm1 * nm0;
 
     // ---- cov_gl, mean_cov_model.h:166-176 ----
     double n_gl =
-        (bg * bl) / ebgl + Cgl / ebgl + (bg * ml) / ebt - (bg * ml) / ebgl
+        (bg * bl) / ebgl_ + Cgl / ebgl_ + (bg * ml) / ebt_ - (bg * ml) / ebgl_
         + Cll * mq * jB_c1l.I[1] + Clq * ml * jBm_c1.I[1]
         + (bq * Cll + bl * Clq + Clq * Cxl + Cll * Cxq - Clq * ml - Cll * mq) * jBm_c1l.I[1]
         + Cll * Clq * jBm_c1l.I[2] + ml * mq * jB_c1.I[0]
@@ -330,15 +335,15 @@ GGP_HD void ggp_propagate_impl(GgpState& s, double t, const GgpOuParams& p, cons
         const GgpInts<0> jBp_c1qw = ggp_load_ints<0>(S, 6);
         n_gq =
         n_gq =
-            (bg * bq) / ebgq + Cgq / ebgq + (bg * mq) / ebt - (bg * mq) / ebgq
+            (bg * bq) / ebgq_ + Cgq / ebgq_ + (bg * mq) / ebt_ - (bg * mq) / ebgq_
             + Clq * mq * jB_c1q.I[1] + Clq * mq * jBm_c1.I[1]
             + (2 * bq * Clq + 2 * Clq * Cxq - 2 * Clq * mq) * jBm_c1q.I[1]
             + (Clq * Clq) * jBm_c1q.I[2] + (mq * mq) * jB_c1.I[0]
             + (bq * mq + Cxq * mq - (mq * mq)) * jB_c1q.I[0]
             + (bq * mq + Cxq * mq - (mq * mq)) * jBm_c1.I[0]
-            - (sq2 * jBm_c1qw.I[0]) / (2. * gq)
+            - (sq2 * jBm_c1qw.I[0]) / two_gq_
             + ((bq * bq) + Cqq + 2 * bq * Cxq + (Cxq * Cxq) - 2 * bq * mq - 2 * Cxq * mq + (mq * mq)) * jBm_c1q.I[0]
-            + (sq2 * jBp_c1qw.I[0]) / (2. * gq)
+            + (sq2 * jBp_c1qw.I[0]) / two_gq_
             - nm1 * nm3;
     }
 
@@ -357,48 +362,48 @@ GGP_HD void ggp_propagate_impl(GgpState& s, double t, const GgpOuParams& p, cons
         n_gg =
             ((bg * bg) + Cgg) / e2bt
             + 2 * Cgl * mq * jB_c2.I[1]
-            + (mq * (2 * Clq + gq * mq) * jW_lo.I[1]) / gq
+            + (mq * (2 * Clq + gq * mq) * jW_lo.I[1]) / gq_
             + 2 * (bq * Cgl + bg * Clq + Clq * Cxg + Cgl * Cxq - Cgl * mq) * jBm_c2.I[1]
             + ((bq2 * gq + Cqq * gq + 4 * bq * Cxq * gq + 4 * Cxq2 * gq - 2 * Clq * mq - 2 * bq * gq * mq
-                - 4 * Cxq * gq * mq + gq * mq2) * jWm_lo.I[1]) / gq
+                - 4 * Cxq * gq * mq + gq * mq2) * jWm_lo.I[1]) / gq_
             - mq2 * jW_hi.I[1]
-            - (2 * Clq * mq * jW_d2.I[1]) / gq
-            - (sq2 * jWm_lo.I[1]) / (2. * gq)
-            + (sq2 * jWm_hi.I[1]) / (2. * gq)
+            - (2 * Clq * mq * jW_d2.I[1]) / gq_
+            - (sq2 * jWm_lo.I[1]) / two_gq_
+            + (sq2 * jWm_hi.I[1]) / two_gq_
             + (-bq2 - Cqq - 4 * bq * Cxq - 4 * Cxq2 + 2 * bq * mq + 4 * Cxq * mq - mq2 + 4 * bq * Clq * t
                + 8 * Clq * Cxq * t - 4 * Clq * mq * t) * jWm_hi.I[1]
-            + (2 * Clq * mq * jWm_d3.I[1]) / gq
+            + (2 * Clq * mq * jWm_d3.I[1]) / gq_
             + Clq2 * jWm_lo.I[3]
             - Clq2 * jWm_hi.I[3]
             + 2 * Cgl * Clq * jBm_c2.I[2]
             + (2 * bq * Clq + 4 * Clq * Cxq - 2 * Clq * mq) * jWm_lo.I[2]
             + (-2 * bq * Clq - 4 * Clq * Cxq + 2 * Clq * mq + 2 * Clq2 * t) * jWm_hi.I[2]
             + (2 * bg * mq + 2 * Cxg * mq) * jB_c2.I[0]
-            + ((2 * bq * mq) / gq + (4 * Cxq * mq) / gq - (2 * mq2) / gq) * jW_lo.I[0]
+            + ((2 * bq * mq) / gq_ + (4 * Cxq * mq) / gq_ - (2 * mq2) / gq_) * jW_lo.I[0]
             + (2 * bg * bq + 2 * Cgq + 2 * bq * Cxg + 2 * bg * Cxq + 2 * Cxg * Cxq - 2 * bg * mq - 2 * Cxg * mq) * jBm_c2.I[0]
-            + ((-2 * bq * mq) / gq - (4 * Cxq * mq) / gq + (2 * mq2) / gq) * jWm_lo.I[0]
-            + (sq2 * jW_lo.I[0]) / (2. * gq2)
-            + (sq2 * jW_hi.I[0]) / (2. * gq2)
+            + ((-2 * bq * mq) / gq_ - (4 * Cxq * mq) / gq_ + (2 * mq2) / gq_) * jWm_lo.I[0]
+            + (sq2 * jW_lo.I[0]) / two_gq2_
+            + (sq2 * jW_hi.I[0]) / two_gq2_
             + 2 * mq2 * t * jW_hi.I[0]
-            + ((-2 * bq * mq) / gq - (4 * Cxq * mq) / gq + (2 * mq2) / gq) * jW_d2.I[0]
-            - (sq2 * jWm_lo.I[0]) / (2. * gq2)
-            - (sq2 * t * jWm_hi.I[0]) / gq
+            + ((-2 * bq * mq) / gq_ - (4 * Cxq * mq) / gq_ + (2 * mq2) / gq_) * jW_d2.I[0]
+            - (sq2 * jWm_lo.I[0]) / two_gq2_
+            - (sq2 * t * jWm_hi.I[0]) / gq_
             + (2 * bq2 * t + 2 * Cqq * t + 8 * bq * Cxq * t + 8 * Cxq2 * t - 4 * bq * mq * t - 8 * Cxq * mq * t
                + 2 * mq2 * t) * jWm_hi.I[0]
-            + ((2 * bq * mq) / gq + (4 * Cxq * mq) / gq - (2 * mq2) / gq) * jWm_d3.I[0]
-            - (sq2 * jWp_d4.I[0]) / (2. * gq2)
+            + ((2 * bq * mq) / gq_ + (4 * Cxq * mq) / gq_ - (2 * mq2) / gq_) * jWm_d3.I[0]
+            - (sq2 * jWp_d4.I[0]) / two_gq2_
             - (nm1 * nm1);
     }
 
     // ---- the elementary block, mean_cov_model.h:93-95, 117-122, 196-208 ----
     const double egl2 = egl * egl, egq2 = egq * egq;
-    double n_xx = Cll * (omegl * omegl) / (gl * gl) + 2 * Cxl * omegl / gl + Cxx
+    double n_xx = Cll * (omegl * omegl) / (gl * gl) + 2 * Cxl * omegl / gl_ + Cxx
                   + sl2 / (2 * ggp_pow(gl, 3.0, M)) * (2 * gl * t - 3 + 4 * egl - egl2);
-    double n_xl = sl2 / (2 * (gl * gl)) * (omegl * omegl) + Cll * egl * omegl / gl + Cxl * egl;
-    double n_xq = Clq * omegl * egq / gl + Cxq * egq;
+    double n_xl = sl2 / (2 * (gl * gl)) * (omegl * omegl) + Cll * egl * omegl / gl_ + Cxl * egl;
+    double n_xq = Clq * omegl * egq / gl_ + Cxq * egq;
     double n_ll = Cll * egl2 + sl2 / (2 * gl) * (1 - egl2);
     double n_lq = Clq * egl * egq;
-    double n_qq = sq2 / (2 * gq) * (1 - egq2) + Cqq * egq2;
+    double n_qq = sq2 / two_gq_ * (1 - egq2) + Cqq * egq2;
 
     s.m[0] = nm0; s.m[1] = nm1; s.m[2] = nm2; s.m[3] = nm3;
     s.c[0] = n_xx; s.c[1] = n_xg; s.c[2] = n_xl; s.c[3] = n_xq; s.c[4] = n_gg;

@@ -133,7 +133,8 @@ const char* ggp_last_error(void);
 const char* ggp_version(void);
 
 /* device self-test of the strict math (exp/log/pow/Dawson/propagate) for callers that hold expected bits:
- * evaluates fn over n inputs on the device.  fn: 0 exp, 1 log, 2 pow(x, y), 3 dawson.  y may be NULL. */
+ * evaluates fn over n inputs on the device.  fn: 0 exp, 1 log, 2 pow(x, y), 3 dawson, 4 x / y through the shared-reciprocal
+ * divisor path (GgpDivisor).  y may be NULL for 0, 1, 3. */
 int ggp_math_eval(int32_t device, int32_t fn, int64_t n, const double* x, const double* y, double* out);
 /* propagate n independent states (14 doubles each: 4 means + upper triangle) over dt[i] with 7 OU params each
  * (mean_cov_model, mean_cov_model.h:211); cross (NULL or [n][16]) receives cross_cov_model (:380). */

@@ -36,6 +36,24 @@ def test_device_math_bits(golden_dir):
     assert same_bits(api.math_eval("dawson", xs), np.array([L.ggp_oracle_dawson(v) for v in xs]))
 
 
+def test_shared_reciprocal_division_is_ieee():
+    """a / GgpDivisor(b) must be the correctly rounded quotient (what the host's `/` returns) for every operand
+    class: the step's ~190 divisions per time point go through it"""
+    rng = np.random.default_rng(4)
+    n = 400000
+    a = rng.standard_normal(n) * 10 ** rng.uniform(-300, 300, n)
+    b = rng.standard_normal(n) * 10 ** rng.uniform(-300, 300, n)
+    a2 = rng.standard_normal(n) * 10 ** rng.uniform(-12, 12, n)
+    b2 = rng.standard_normal(n) * 10 ** rng.uniform(-12, 12, n)
+    sp = np.array([0.0, -0.0, 1.0, np.inf, -np.inf, np.nan, 5e-324, 1e-310, 1.7e308, 2.2250738585072014e-308, 3.0, 1 / 3])
+    a3, b3 = [v.reshape(-1) for v in np.meshgrid(sp, sp)]
+    a = np.concatenate([a, a2, a3, b2 * (1 + 2.0 ** -52)])
+    b = np.concatenate([b, b2, b3, b2])
+    with np.errstate(all="ignore"):
+        ref = a / b
+    assert same_bits(api.math_eval("div", a, b), ref)
+
+
 def test_device_step_matches_reference_golden(golden_dir):
     z = np.load(os.path.join(golden_dir, "ref_step_vectors.npz"))
     iu = np.triu_indices(4)

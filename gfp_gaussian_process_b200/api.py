@@ -128,6 +128,30 @@ def prediction_forward_backward(forest: Forest, params_vecs, forward=True, backw
     return {k: (a[:, :4], a[:, 4:].reshape(M, 4, 4)) for k, a in bufs.items() if a is not None}
 
 
+def collect_joint_distributions(forest: Forest, params_vecs, tolerance_joint=1e-10, row_begin=0, row_end=None, cap=None):
+    """collect_joint_distributions (correlation_tree.h:629-648) as a sparse list instead of the dense CSV.
+    prediction_forward_backward must have been run on `forest` with the same params_vecs (the reference's -j
+    implies -p, main.cpp:265-268).  Rows are the start points row_begin <= ctp < row_end.
+    Returns (row_ctp, col_ctp, mean [n][8], cov_upper [n][36]), sorted by (row, col): the joint of
+    z at `col` (first four means) and z at `row` (last four), tolerance as --rel_tolerance_joints."""
+    lib = _lib.load()
+    p, _ = _as_params(params_vecs)
+    if row_end is None:
+        row_end = forest.n_ctp
+    cnt = C.c_int64(0)
+    args = (forest.handle, p.ctypes.data_as(_lib.c_double_p), p.shape[0], C.c_double(tolerance_joint), row_begin, row_end)
+    if cap is None:
+        _lib.check(lib.ggp_joints(*args, 0, C.byref(cnt), None, None, None))
+        cap = cnt.value
+    row = np.empty(max(cap, 1), dtype=np.int64)
+    col = np.empty(max(cap, 1), dtype=np.int64)
+    rec = np.empty((max(cap, 1), 44))
+    _lib.check(lib.ggp_joints(*args, cap, C.byref(cnt), row.ctypes.data_as(_lib.c_int64_p), col.ctypes.data_as(_lib.c_int64_p),
+                              rec.ctypes.data_as(_lib.c_double_p)))
+    n = min(cnt.value, cap)
+    return row[:n], col[:n], rec[:n, :8], rec[:n, 8:]
+
+
 def backward_cell_state(forest: Forest):
     """each cell's MOMAdata::mean/cov as the backward pass leaves them (sign-flipped frame)."""
     lib = _lib.load()

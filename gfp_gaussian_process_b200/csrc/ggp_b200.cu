@@ -81,7 +81,9 @@ struct ggp_forest {
     // workspaces
     DevBuf<double> w_params, w_state, w_partial, w_out, w_cell_ll, w_carry;
     DevBuf<unsigned long long> w_nan;
-    DevBuf<double> fwd, bwd, comb, bstate, pred_params;
+    DevBuf<double> fwd, bwd, comb, bstate, pred_params, prep, jstack;
+    DevBuf<int32_t> ctp_slot, jstack_slot;
+    bool have_prep = false;
     bool have_pred = false;
     int32_t pred_n_seg = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -116,6 +118,7 @@ cudaError_t opt_in_smem() {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(ggp_forward_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GGP_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(ggp_forward_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GGP_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(ggp_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GGP_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ggp_joint_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GGP_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(ggp_propagate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GGP_SMEM_BYTES);
     return e;
 }
@@ -177,6 +180,7 @@ int ggp_forest_create(const ggp_forest_desc* d, ggp_forest** out) {
     if (e == cudaSuccess) e = f->s_d2.upload(L.s_d2, s);
     if (e == cudaSuccess) e = f->s_root.upload(L.s_root, s);
     if (e == cudaSuccess) e = f->s_cell.upload(L.s_cell, s);
+    if (e == cudaSuccess) e = f->ctp_slot.upload(L.ctp_slot, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     if (e == cudaSuccess) e = cudaEventCreate(&f->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&f->ev1);
@@ -194,9 +198,9 @@ void ggp_forest_destroy(ggp_forest* f) {
     cudaSetDevice(f->device);
     cudaDeviceSynchronize();
     for (DevBuf<double>* b : {&f->time, &f->x, &f->g, &f->w_params, &f->w_state, &f->w_partial, &f->w_out, &f->w_cell_ll,
-                              &f->w_carry, &f->fwd, &f->bwd, &f->comb, &f->bstate, &f->pred_params})
+                              &f->w_carry, &f->fwd, &f->bwd, &f->comb, &f->bstate, &f->pred_params, &f->prep, &f->jstack})
         b->release();
-    for (DevBuf<int32_t>* b : {&f->seg, &f->comb_seg, &f->s_n, &f->s_parent, &f->s_d1, &f->s_d2, &f->s_root, &f->s_cell})
+    for (DevBuf<int32_t>* b : {&f->seg, &f->comb_seg, &f->s_n, &f->s_parent, &f->s_d1, &f->s_d2, &f->s_root, &f->s_cell, &f->ctp_slot, &f->jstack_slot})
         b->release();
     f->s_off.release();
     f->s_dfs0.release();
@@ -221,6 +225,7 @@ int ggp_forest_upload_series(ggp_forest* f, const double* time, const double* lo
     GGP_CUDA(cudaMemcpyAsync(f->x.p, log_length, b, cudaMemcpyHostToDevice, f->stream));
     GGP_CUDA(cudaMemcpyAsync(f->g.p, fp, b, cudaMemcpyHostToDevice, f->stream));
     f->have_pred = false;
+    f->have_prep = false;
     return GGP_OK;
 }
 
@@ -378,6 +383,7 @@ int ggp_predict(ggp_forest* f, const double* params, int32_t n_seg, double* out_
     GGP_CUDA(cudaMemcpyAsync(f->pred_params.p, params, (size_t)n_seg * GGP_NP * sizeof(double), cudaMemcpyHostToDevice, s));
     f->pred_n_seg = n_seg;
     f->have_pred = false;
+    f->have_prep = false;
     f->last_launches = 0;
     const GgpDevForest F = f->dev();
     GGP_CUDA(cudaEventRecord(f->ev0, s));

@@ -1,2 +1,502 @@
-// ggp_joints.cuh — placeholder until the joints kernels land
+// ggp_joints.cuh — pairwise joint posteriors P(z_{n+m}, z_n | D) along the lineage (the reference's -j mode).
+//
+// Replaces, from the reference (paths under src/):
+//   Gaussian / Affine_gaussian / Seperated_gaussian, seperate_gaussian, flip_xy      Gaussians.h:24-158
+//   include_measurement                                                              correlation_tree.h:132-154
+//   consecutive_joint[_cell_division], consecutive_conditional[_cell_division]       correlation_tree.h:160-396
+//   calc_x / calc_X / calc_Y / propagation / next_joint                              correlation_tree.h:403-454
+//   incorporate_backward_prob, crosscovariance_is_small                              correlation_tree.h:457-493
+//   calc_joint_distributions, joint_distributions_recr, sc_joint_distributions       correlation_tree.h:499-626
+//
+// The reference recomputes, for every start point n, the conditional P(z_{k+1} | z_k, D_k) of every later
+// point k it passes (one mean_cov_model + one cross_cov_model each time) and keeps 8x8 Eigen matrices on
+// the heap.  Here the two quantities that depend on a single point only — the first joint
+// J0(k) = P(z_{k+1}, z_k | D_k) and the transformed conditional — are computed ONCE per cell-timepoint by a
+// first kernel (ggp_ctp_joint_prep: one propagation step with cross covariance per point) and cached in HBM;
+// a second kernel gives one thread to every start point, walks forward in time and depth-first into both
+// daughters with the 8-dim Gaussian in registers/local memory and an explicit stack of pending daughter
+// branches, and appends the joints it emits to a sparse list.
+// Eigen semantics kept: dynamic inverses = partial-pivot LU (also the 2x2 of
+// include_measurement, which inverts a MatrixXd), dynamic products coefficient-wise left to right, matrix *
+// vector = column-major GEMV (four columns at a time, remaining columns one by one).
+// Host+device; compile with FMA contraction off.
 #pragma once
+#include "ggp_cell.cuh"
+
+struct GgpGauss4 { double m[4]; double C[16]; };
+struct GgpAffine { double a[4]; double F[16]; double A[16]; };   // N(y | a + F x, A)
+struct GgpGauss8 { double m[8]; double C[64]; };
+struct GgpSep { GgpGauss4 marg; GgpAffine cond; };
+
+#define GGP_JOINT_PREP 108   // doubles cached per ctp: J0 (8 + 64) then the conditional (4 + 16 + 16)
+
+// C = op(A) * op(B), 4x4, coefficient-wise, inner sum left to right
+template <bool TA, bool TB>
+GGP_HD void ggp_mm4(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            double s = (TA ? A[i] : A[4 * i]) * (TB ? B[4 * j] : B[j]);
+#pragma unroll
+            for (int k = 1; k < 4; ++k) s = s + (TA ? A[4 * k + i] : A[4 * i + k]) * (TB ? B[4 * j + k] : B[4 * k + j]);
+            C[4 * i + j] = s;
+        }
+}
+
+GGP_HD void ggp_gemv4t(const double* __restrict__ A, const double* __restrict__ x, double* __restrict__ y) {   // y = A x
+    ggp_gemv4(A, x, y);
+}
+
+// seperate_gaussian (Gaussians.h:127-145): N([x y] | m, C) -> N(x | a, A) N(y | b' + F x, B')
+GGP_HD void ggp_separate(const GgpGauss8& J, GgpSep& S) {
+    double A[16], K[16], B[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            A[4 * i + j] = J.C[8 * i + j];
+            K[4 * i + j] = J.C[8 * i + 4 + j];
+            B[4 * i + j] = J.C[8 * (4 + i) + 4 + j];
+        }
+    double Ai[16], KtAi[16], t[4], KAK[16];
+    ggp_inv_lu<4>(A, Ai);
+    ggp_mm4<true, false>(K, Ai, KtAi);
+    ggp_gemv4(KtAi, J.m, t);
+    ggp_mm4<false, false>(KtAi, K, KAK);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        S.marg.m[i] = J.m[i];
+        S.cond.a[i] = J.m[4 + i] - t[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        S.marg.C[i] = A[i];
+        S.cond.F[i] = KtAi[i];
+        S.cond.A[i] = B[i] - KAK[i];
+    }
+}
+
+// Seperated_gaussian::to_joint (Gaussians.h:109-124): N(x | m, C) N(y | a + F x, A) -> N([x y] | ., .)
+GGP_HD void ggp_to_joint(const GgpGauss4& g, const GgpAffine& c, GgpGauss8& J) {
+    double Fm[4], CtFt[16], FC[16], FCt[16], FCtFt[16];
+    ggp_gemv4(c.F, g.m, Fm);
+    ggp_mm4<true, true>(g.C, c.F, CtFt);
+    ggp_mm4<false, false>(c.F, g.C, FC);
+    ggp_mm4<false, true>(c.F, g.C, FCt);
+    ggp_mm4<false, true>(FCt, c.F, FCtFt);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        J.m[i] = g.m[i];
+        J.m[4 + i] = c.a[i] + Fm[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            J.C[8 * i + j] = g.C[4 * i + j];
+            J.C[8 * i + 4 + j] = CtFt[4 * i + j];
+            J.C[8 * (4 + i) + j] = FC[4 * i + j];
+            J.C[8 * (4 + i) + 4 + j] = c.A[4 * i + j] + FCtFt[4 * i + j];
+        }
+}
+
+// Gaussian::flip_xy (Gaussians.h:147-158)
+GGP_HD void ggp_flip_xy(const GgpGauss8& J, GgpGauss8& R) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { R.m[i] = J.m[4 + i]; R.m[4 + i] = J.m[i]; }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            R.C[8 * i + j] = J.C[8 * (4 + i) + 4 + j];
+            R.C[8 * i + 4 + j] = J.C[8 * j + 4 + i];          // C.block(0,n,n,n)^T
+            R.C[8 * (4 + i) + j] = J.C[8 * (4 + j) + i];      // C.block(n,0,n,n)^T
+            R.C[8 * (4 + i) + 4 + j] = J.C[8 * i + j];
+        }
+}
+
+// Gaussian::multiply (Gaussians.h:42-49)
+GGP_HD void ggp_gauss_multiply(const GgpGauss4& n1, const GgpGauss4& n2, GgpGauss4& out) {
+    double S[16], Si[16], C2Si[16], C1Si[16], a[4], b[4];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) S[i] = n1.C[i] + n2.C[i];
+    ggp_inv_lu<4>(S, Si);
+    ggp_mm4<false, false>(n2.C, Si, C2Si);
+    ggp_mm4<false, false>(n1.C, Si, C1Si);
+    ggp_gemv4(C2Si, n1.m, a);
+    ggp_gemv4(C1Si, n2.m, b);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) out.m[i] = a[i] + b[i];
+    ggp_mm4<false, false>(C1Si, n2.C, out.C);
+}
+
+// Affine_gaussian::transform() (Gaussians.h:71-81): N(y | a + F x, A) -> N(x | a' + F' y, A')
+GGP_HD void ggp_affine_transform(const GgpAffine& c, GgpAffine& out) {
+    double Fi[16], t[4], FiA[16];
+    ggp_inv_lu<4>(c.F, Fi);
+    ggp_gemv4(Fi, c.a, t);
+    ggp_mm4<false, false>(Fi, c.A, FiA);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) out.a[i] = -t[i];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) out.F[i] = Fi[i];
+    ggp_mm4<false, true>(FiA, Fi, out.A);
+}
+
+// include_measurement (correlation_tree.h:132-154) on the 8-dim joint; D = diag(D00, D11)
+GGP_HD void ggp_include_measurement(GgpGauss8& J, double D00, double D11, double x, double g) {
+    double S[4] = {J.C[0] + D00, J.C[1] + 0.0, J.C[8] + 0.0, J.C[9] + D11}, Si[4];
+    const double xg0 = x - J.m[0], xg1 = g - J.m[1];
+    ggp_inv_lu<2>(S, Si);
+    double T0[8], T1[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        T0[i] = J.C[i] * Si[0] + J.C[8 + i] * Si[2];
+        T1[i] = J.C[i] * Si[1] + J.C[8 + i] * Si[3];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) J.m[i] = J.m[i] + ((0.0 + T0[i] * xg0) + T1[i] * xg1);
+    double K0[8], K1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { K0[j] = J.C[j]; K1[j] = J.C[8 + j]; }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) J.C[8 * i + j] = J.C[8 * i + j] - (T0[i] * K0[j] + T1[i] * K1[j]);
+}
+
+// next_joint (correlation_tree.h:426-454): P(z_{k+1}, z_n | D_{k+1}) x P(z_{k+2} | z_{k+1}, D_{k+1}) -> P(z_{k+2}, z_n | D_{k+1})
+GGP_HD void ggp_next_joint(const GgpGauss8& J, const GgpAffine& cond, GgpGauss8& out) {
+    GgpSep sep;
+    ggp_separate(J, sep);
+    // calc_x / calc_X / calc_Y (correlation_tree.h:403-415)
+    double S[16], Si[16], ASi[16], CSi[16], u[4], v[4];
+    GgpAffine NX;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) S[i] = sep.marg.C[i] + cond.A[i];
+    ggp_inv_lu<4>(S, Si);
+    ggp_mm4<false, false>(cond.A, Si, ASi);
+    ggp_mm4<false, false>(sep.marg.C, Si, CSi);
+    ggp_gemv4(ASi, sep.marg.m, u);
+    ggp_gemv4(CSi, cond.a, v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) NX.a[i] = u[i] + v[i];
+    ggp_mm4<false, false>(CSi, cond.F, NX.F);
+    ggp_mm4<false, false>(CSi, cond.A, NX.A);
+    // G.transform(marginal.m) (Gaussians.h:83-87) with G = (cond.a, cond.F, marginal.C + cond.A)
+    GgpGauss4 nm;
+    {
+        double Fi[16], d[4], FiA[16];
+        ggp_inv_lu<4>(cond.F, Fi);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) d[i] = sep.marg.m[i] - cond.a[i];
+        ggp_gemv4(Fi, d, nm.m);
+        ggp_mm4<false, false>(Fi, S, FiA);
+        ggp_mm4<false, true>(FiA, Fi, nm.C);
+    }
+    // propagation(sep.conditional, NX) (correlation_tree.h:418-423)
+    GgpAffine nc;
+    {
+        double Fx[4], FA[16], FAFt[16];
+        ggp_gemv4(sep.cond.F, NX.a, Fx);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) nc.a[i] = sep.cond.a[i] + Fx[i];
+        ggp_mm4<false, false>(sep.cond.F, NX.F, nc.F);
+        ggp_mm4<false, false>(sep.cond.F, NX.A, FA);
+        ggp_mm4<false, true>(FA, sep.cond.F, FAFt);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) nc.A[i] = sep.cond.A[i] + FAFt[i];
+    }
+    ggp_to_joint(nm, nc, out);
+}
+
+// incorporate_backward_prob (correlation_tree.h:457-482); mb/Cb = stored backward prediction at the point
+GGP_HD void ggp_incorporate_backward(const GgpGauss8& J, const double* __restrict__ mb, const double* __restrict__ Cb,
+                                     const double* __restrict__ p, GgpGauss8& out) {
+    GgpSep sep;
+    ggp_separate(J, sep);
+    GgpGauss4 bw;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) bw.m[i] = mb[i];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) bw.C[i] = Cb[i];
+    ggp_divide_by_prior(bw.m, bw.C, p);
+    GgpGauss4 marg;
+    ggp_gauss_multiply(sep.marg, bw, marg);
+    ggp_to_joint(marg, sep.cond, out);
+}
+
+// crosscovariance_is_small (correlation_tree.h:484-493); a NaN ratio counts as small, as there
+GGP_HD bool ggp_crosscov_small(const GgpGauss8& J, double tol) {
+    bool small = true;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 4; j < 8; ++j)
+            if (fabs(J.C[8 * i + j] / (J.m[i] * J.m[j])) > tol) small = false;
+    return small;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-ctp preparation: J0(k) = P(z_{k+1}, z_k | D_k) (consecutive_joint, correlation_tree.h:325-357, or
+// consecutive_joint_cell_division :160-238 at a cell's last point) and the transformed conditional
+// (consecutive_conditional :360-396 / _cell_division :241-319), from the forward posterior at k.
+// prep = [J0.m 8][J0.C 64][cond.a 4][cond.F 16][cond.A 16]; nothing is written for the last point of a leaf.
+// ------------------------------------------------------------------------------------------------
+struct GgpJointArgs {
+    const double* params;    // [n_seg][11]
+    const double* fwd;       // [n_ctp][20]
+    const double* bwd;       // [n_ctp][20]
+    const double* bstate;    // [n_cells][20] by slot
+    double* prep;            // [n_ctp][GGP_JOINT_PREP]
+    const int32_t* ctp_slot; // [n_ctp] slot of the cell a ctp belongs to
+    double tol;
+    // output list
+    int64_t row_begin, row_end;   // start points handled by this launch (ctp range)
+    long long cap;
+    unsigned long long* count;
+    long long* row_ctp;
+    long long* col_ctp;
+    double* rec44;
+    double* stack;           // [n_starts][stack_depth][72] pending daughter branches
+    int32_t* stack_slot;     // [n_starts][stack_depth]
+    int stack_depth;
+};
+
+GGP_HD void ggp_ctp_joint_prep(const GgpDevForest& F, const GgpJointArgs& A, int64_t k, const GgpMathTables* __restrict__ T,
+                               const GgpScratch& S) {
+    const int slot = A.ctp_slot[k];
+    const int64_t off = F.s_off[slot];
+    const int n = F.s_n[slot];
+    const int t = (int)(k - off);
+    const bool last = (t == n - 1);
+    const int d1 = F.s_d1[slot];
+    if (last && d1 < 0) return;   // joints starting at / passing a leaf's last point go nowhere
+    const double* p = A.params + GGP_NP * F.seg[k];
+    const double* f = A.fwd + 20 * k;
+    double mean1[4], cov1[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) mean1[i] = f[i];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) cov1[i] = f[4 + i];
+    GgpState s;
+    ggp_state_from16(s, mean1, cov1);
+    GgpGauss8 J0;
+    GgpAffine cond;
+    if (!last) {
+        double cross[16], cov2[16];
+        const double dt = F.time[k + 1] - F.time[k];
+        ggp_propagate_impl(s, dt, ggp_ou(p, false), T, S, cross);
+        ggp_state_to16(s, cov2);
+        GgpGauss8 J2;   // [z_n, z_n+1] for the conditional
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            J0.m[i] = s.m[i]; J0.m[4 + i] = mean1[i];
+            J2.m[i] = mean1[i]; J2.m[4 + i] = s.m[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                J0.C[8 * i + j] = cov2[4 * i + j];
+                J0.C[8 * i + 4 + j] = cross[4 * i + j];
+                J0.C[8 * (4 + i) + j] = cross[4 * j + i];
+                J0.C[8 * (4 + i) + 4 + j] = cov1[4 * i + j];
+                J2.C[8 * i + j] = cov1[4 * i + j];
+                J2.C[8 * i + 4 + j] = cross[4 * j + i];
+                J2.C[8 * (4 + i) + j] = cross[4 * i + j];
+                J2.C[8 * (4 + i) + 4 + j] = cov2[4 * i + j];
+            }
+        GgpSep sep;
+        ggp_separate(J2, sep);
+        ggp_affine_transform(sep.cond, cond);
+    } else {
+        const double var_dx = p[9], var_dg = p[10];
+        const double log2v = GGP_LOG2;
+        if (F.model.division_binomial) {
+            const double dt = F.time[F.s_off[d1]] - F.time[k];
+            ggp_propagate(s, dt, ggp_ou(p, false), T, S);
+            ggp_divide(s, var_dx, var_dg, F.model);
+            double cov2[16], cross[16];
+            ggp_state_to16(s, cov2);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) cross[i] = cov1[i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) cross[4 + j] = cross[4 + j] / 2.;
+            GgpGauss8 J2;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                J0.m[i] = s.m[i]; J0.m[4 + i] = mean1[i];
+                J2.m[i] = mean1[i]; J2.m[4 + i] = s.m[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    J0.C[8 * i + j] = cov2[4 * i + j];
+                    J0.C[8 * i + 4 + j] = cross[4 * i + j];
+                    J0.C[8 * (4 + i) + j] = cross[4 * j + i];
+                    J0.C[8 * (4 + i) + 4 + j] = cov1[4 * i + j];
+                    J2.C[8 * i + j] = cov1[4 * i + j];
+                    J2.C[8 * i + 4 + j] = cross[4 * j + i];
+                    J2.C[8 * (4 + i) + j] = cross[4 * i + j];
+                    J2.C[8 * (4 + i) + 4 + j] = cov2[4 * i + j];
+                }
+            GgpSep sep;
+            ggp_separate(J2, sep);
+            ggp_affine_transform(sep.cond, cond);
+        } else {
+            // gauss: the model's own conditional N(z_n+1 | f + F z_n, D) (correlation_tree.h:224-236, :302-318)
+            GgpAffine c;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { c.F[i] = 0.0; c.A[i] = 0.0; }
+            c.F[0] = 1.0; c.F[5] = 0.5; c.F[10] = 1.0; c.F[15] = 1.0;
+            c.A[0] = var_dx; c.A[5] = var_dg;
+            c.a[0] = -log2v; c.a[1] = 0.0; c.a[2] = 0.0; c.a[3] = 0.0;
+            GgpGauss4 marg;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) marg.m[i] = mean1[i];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) marg.C[i] = cov1[i];
+            GgpGauss8 Jyx;
+            ggp_to_joint(marg, c, Jyx);
+            ggp_flip_xy(Jyx, J0);
+            ggp_affine_transform(c, cond);
+        }
+    }
+    double* out = A.prep + (int64_t)GGP_JOINT_PREP * k;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) out[i] = J0.m[i];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) out[8 + i] = J0.C[i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) out[72 + i] = cond.a[i];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { out[76 + i] = cond.F[i]; out[92 + i] = cond.A[i]; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// one start point (row): sc_joint_distributions' body for one n (correlation_tree.h:598-616) with
+// joint_distributions_recr / calc_joint_distributions unrolled into a loop with an explicit stack
+// ------------------------------------------------------------------------------------------------
+GGP_HD void ggp_emit_joint(const GgpJointArgs& A, int64_t row, int64_t col, const GgpGauss8& J) {
+#if defined(__CUDA_ARCH__)
+    const unsigned long long idx = atomicAdd(A.count, 1ull);
+#else
+    const unsigned long long idx = (*A.count)++;
+#endif
+    if ((long long)idx >= A.cap) return;
+    A.row_ctp[idx] = row;
+    A.col_ctp[idx] = col;
+    double* r = A.rec44 + 44 * idx;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[i] = J.m[i];
+    int q = 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = i; j < 8; ++j) r[q++] = J.C[8 * i + j];
+}
+
+GGP_HD void ggp_load_joint(const double* __restrict__ src, GgpGauss8& J) {
+    for (int i = 0; i < 8; ++i) J.m[i] = src[i];
+    for (int i = 0; i < 64; ++i) J.C[i] = src[8 + i];
+}
+GGP_HD void ggp_store_joint(double* __restrict__ dst, const GgpGauss8& J) {
+    for (int i = 0; i < 8; ++i) dst[i] = J.m[i];
+    for (int i = 0; i < 64; ++i) dst[8 + i] = J.C[i];
+}
+
+GGP_HD void ggp_start_point_joints(const GgpDevForest& F, const GgpJointArgs& A, int64_t row, int64_t start_index) {
+    const int slot0 = A.ctp_slot[row];
+    const int n0 = (int)(row - F.s_off[slot0]);
+    const bool at_division = (n0 == F.s_n[slot0] - 1);
+    if (at_division && F.s_d1[slot0] < 0 && F.s_d2[slot0] < 0) return;   // last point of a leaf: empty row
+    double* stack = A.stack + (int64_t)start_index * A.stack_depth * 72;
+    int32_t* stack_slot = A.stack_slot + (int64_t)start_index * A.stack_depth;
+    int sp = 0;
+    GgpGauss8 J, comb;
+    ggp_load_joint(A.prep + (int64_t)GGP_JOINT_PREP * row, J);
+    int slot = slot0;
+    int t;   // index of the point the joint's first half refers to, inside `slot`
+    if (!at_division) {
+        t = n0 + 1;
+    } else {
+        // consecutive_joint_cell_division needs daughter1 (correlation_tree.h:606-612); both daughters start from it
+        if (F.s_d1[slot0] < 0) return;
+        if (F.s_d2[slot0] >= 0) {
+            ggp_store_joint(stack, J);
+            stack_slot[0] = F.s_d2[slot0];
+            sp = 1;
+        }
+        slot = F.s_d1[slot0];
+        t = 0;
+    }
+    for (;;) {
+        // ---- calc_joint_distributions on `slot` from index t (correlation_tree.h:499-558) ----
+        const int64_t off = F.s_off[slot];
+        const int n = F.s_n[slot];
+        const double stale_g = A.bstate[20 * (int64_t)slot + 1];   // MOMAdata::mean(1) left by the backward pass
+        bool stop = false;
+        for (; t < n; ++t) {
+            const int64_t k = off + t;
+            const double* p = A.params + GGP_NP * F.seg[k];
+            const double D11 = F.model.noise_scaled ? p[8] * (stale_g + F.model.fp_auto) : p[8];
+            ggp_include_measurement(J, p[7], D11, F.x[k], F.g[k]);
+            ggp_incorporate_backward(J, A.bwd + 20 * k, A.bwd + 20 * k + 4, p, comb);
+            if (ggp_crosscov_small(comb, A.tol)) { stop = true; break; }
+            ggp_emit_joint(A, row, k, comb);
+            if (t < n - 1 || F.s_d1[slot] >= 0) {
+                const double* c = A.prep + (int64_t)GGP_JOINT_PREP * k + 72;
+                GgpAffine cond;
+                for (int i = 0; i < 4; ++i) cond.a[i] = c[i];
+                for (int i = 0; i < 16; ++i) { cond.F[i] = c[4 + i]; cond.A[i] = c[20 + i]; }
+                GgpGauss8 nx;
+                ggp_next_joint(J, cond, nx);
+                J = nx;
+            }
+        }
+        if (!stop) {
+            // into the daughters (joint_distributions_recr, correlation_tree.h:566-585): daughter1 first
+            const int d1 = F.s_d1[slot], d2 = F.s_d2[slot];
+            if (d1 >= 0) {
+                if (d2 >= 0 && sp < A.stack_depth) {
+                    ggp_store_joint(stack + (int64_t)sp * 72, J);
+                    stack_slot[sp] = d2;
+                    ++sp;
+                }
+                slot = d1;
+                t = 0;
+                continue;
+            }
+            if (d2 >= 0) {   // daughter2 without daughter1: it keeps whatever joint it had; unreachable with build_cell_genealogy
+                slot = d2;
+                t = 0;
+                continue;
+            }
+        }
+        if (sp == 0) break;
+        --sp;
+        ggp_load_joint(stack + (int64_t)sp * 72, J);
+        slot = stack_slot[sp];
+        t = 0;
+    }
+}
+
+#if defined(__CUDACC__)
+// ---- kernels: one thread per ctp (preparation), one thread per start point (walk) ----
+__global__ void __launch_bounds__(GGP_BLOCK) ggp_joint_prep_kernel(const GgpDevForest F, const GgpJointArgs A) {
+    GgpMathTables& T = *reinterpret_cast<GgpMathTables*>(ggp_smem);
+    ggp_stage_tables(&T);
+    const int64_t k = (int64_t)blockIdx.x * GGP_BLOCK + threadIdx.x;
+    if (k >= F.n_ctp) return;
+    ggp_ctp_joint_prep(F, A, k, &T, ggp_thread_scratch());
+}
+
+__global__ void __launch_bounds__(64) ggp_joint_walk_kernel(const GgpDevForest F, const GgpJointArgs A) {
+    const int64_t i = (int64_t)blockIdx.x * 64 + threadIdx.x;
+    if (A.row_begin + i >= A.row_end) return;
+    ggp_start_point_joints(F, A, A.row_begin + i, i);
+}
+#endif

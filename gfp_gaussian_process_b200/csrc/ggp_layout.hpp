@@ -25,7 +25,7 @@ struct GgpLayout {
     std::vector<int64_t> s_off, s_dfs0;
     std::vector<int32_t> s_n, s_parent, s_d1, s_d2, s_root, s_cell;
     // per ctp
-    std::vector<int32_t> seg, comb_seg;
+    std::vector<int32_t> seg, comb_seg, ctp_slot;
     double init_f[4] = {0, 0, 0, 0}, init_r[4] = {0, 0, 0, 0};
 
     // init_cells_f / init_cells_r (moma_input.h:663-735): left-to-right sums over the cells with more than
@@ -171,6 +171,9 @@ struct GgpLayout {
             if (seg[i] < 0) return "negative segment index";
             max_seg = std::max(max_seg, seg[i]);
         }
+        ctp_slot.assign(d->n_ctp, 0);
+        for (int64_t s = 0; s < N; ++s)
+            for (int64_t k = s_off[s]; k < s_off[s] + s_n[s]; ++k) ctp_slot[k] = (int32_t)s;
         comb_seg = seg;
         for (int64_t c = 0; c < N; ++c)
             if (d->parent[c] >= 0) comb_seg[d->cell_offset[c]] = seg[d->cell_offset[d->parent[c] + 1] - 1];

@@ -109,11 +109,14 @@ int ggp_loglik_device(ggp_forest* f, const double* d_params, int32_t n_vec, doub
 int ggp_predict(ggp_forest* f, const double* params, int32_t n_seg,
                 double* out_forward, double* out_backward, double* out_combined);
 
-/* replaces: collect_joint_distributions (correlation_tree.h:629-648) with a sparse result:
- * record r = (row_ctp[r], col_ctp[r], rec[r][44]) with 8 means (z_{n+m}, z_n) and the 36 upper-triangular
- * covariances row-major, in the reference's emission order.  Requires a prior ggp_predict on the handle.
- * Call with cap = 0 to get the count. */
-int ggp_joints(ggp_forest* f, const double* params, int32_t n_seg, double rel_tol,
+/* replaces: collect_joint_distributions (correlation_tree.h:629-648) with a sparse result: record r =
+ * (row_ctp[r], col_ctp[r], rec[r][44]): the joint P(z_col, z_row | D) as 8 means (z_col then z_row) and the 36
+ * upper-triangular covariances row-major, sorted by (row, col) = the order the reference writes its dense CSV in.
+ * Rows are the start points row_begin <= ctp < row_end, so a caller can stream the matrix in row blocks like the
+ * reference streams lines (the dense row of the example data set alone is 22 065 x 44 fields).  Requires a prior
+ * ggp_predict on the handle with the same params.  *out_count receives the number of joints the rows hold; at most
+ * `cap` are written (call with cap = 0 to size the buffers). */
+int ggp_joints(ggp_forest* f, const double* params, int32_t n_seg, double rel_tol, int64_t row_begin, int64_t row_end,
                int64_t cap, int64_t* out_count, int64_t* row_ctp, int64_t* col_ctp, double* rec44);
 
 /* waits for the evaluation enqueued by ggp_loglik_device and returns its device time in milliseconds */

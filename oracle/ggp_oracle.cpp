@@ -544,3 +544,381 @@ void ggp_oracle_combine_predictions(const ggp_oracle_forest* f, const double* pa
 }
 
 }  // extern "C"
+
+// ================================================================================================
+// joints (correlation_tree.h, Gaussians.h) — restated with small dynamic matrices, like the reference
+// ================================================================================================
+namespace {
+
+struct Mat {   // row-major dynamic matrix, at most 8x8
+    int r = 0, c = 0;
+    double v[64];
+    Mat() {}
+    Mat(int r_, int c_) : r(r_), c(c_) { for (int i = 0; i < r * c; ++i) v[i] = 0.0; }
+    double& operator()(int i, int j) { return v[i * c + j]; }
+    double operator()(int i, int j) const { return v[i * c + j]; }
+};
+struct Vec {
+    int n = 0;
+    double v[8];
+    Vec() {}
+    explicit Vec(int n_) : n(n_) { for (int i = 0; i < n; ++i) v[i] = 0.0; }
+    double& operator()(int i) { return v[i]; }
+    double operator()(int i) const { return v[i]; }
+};
+
+Mat mat4(const double* p) { Mat m(4, 4); for (int i = 0; i < 16; ++i) m.v[i] = p[i]; return m; }
+Vec vec4(const double* p) { Vec x(4); for (int i = 0; i < 4; ++i) x.v[i] = p[i]; return x; }
+
+Mat T(const Mat& a) { Mat t(a.c, a.r); for (int i = 0; i < a.r; ++i) for (int j = 0; j < a.c; ++j) t(j, i) = a(i, j); return t; }
+Mat add(const Mat& a, const Mat& b) { Mat m(a.r, a.c); for (int i = 0; i < a.r * a.c; ++i) m.v[i] = a.v[i] + b.v[i]; return m; }
+Mat sub(const Mat& a, const Mat& b) { Mat m(a.r, a.c); for (int i = 0; i < a.r * a.c; ++i) m.v[i] = a.v[i] - b.v[i]; return m; }
+Vec add(const Vec& a, const Vec& b) { Vec m(a.n); for (int i = 0; i < a.n; ++i) m.v[i] = a.v[i] + b.v[i]; return m; }
+Vec sub(const Vec& a, const Vec& b) { Vec m(a.n); for (int i = 0; i < a.n; ++i) m.v[i] = a.v[i] - b.v[i]; return m; }
+Vec neg(const Vec& a) { Vec m(a.n); for (int i = 0; i < a.n; ++i) m.v[i] = -a.v[i]; return m; }
+
+// MatrixXd * MatrixXd for these sizes: lazy coefficient product, inner sum left to right
+Mat mul(const Mat& a, const Mat& b) {
+    Mat m(a.r, b.c);
+    for (int i = 0; i < a.r; ++i)
+        for (int j = 0; j < b.c; ++j) {
+            double s = a(i, 0) * b(0, j);
+            for (int k = 1; k < a.c; ++k) s += a(i, k) * b(k, j);
+            m(i, j) = s;
+        }
+    return m;
+}
+// MatrixXd * VectorXd: column-major GEMV, four columns at a time, the remaining ones one by one
+Vec mul(const Mat& a, const Vec& x) {
+    Vec y(a.r);
+    int j = 0;
+    for (; j + 4 <= a.c; j += 4)
+        for (int i = 0; i < a.r; ++i)
+            y(i) = y(i) + ((a(i, j) * x(j) + a(i, j + 1) * x(j + 1)) + (a(i, j + 2) * x(j + 2) + a(i, j + 3) * x(j + 3)));
+    for (; j < a.c; ++j)
+        for (int i = 0; i < a.r; ++i) y(i) = y(i) + a(i, j) * x(j);
+    return y;
+}
+Mat inverse(const Mat& a) {
+    Mat m(a.r, a.c);
+    if (a.r == 2) inv_lu<2>(a.v, m.v);
+    else inv_lu<4>(a.v, m.v);
+    return m;
+}
+Mat block(const Mat& a, int i0, int j0, int r, int c) {
+    Mat m(r, c);
+    for (int i = 0; i < r; ++i) for (int j = 0; j < c; ++j) m(i, j) = a(i0 + i, j0 + j);
+    return m;
+}
+Vec head(const Vec& a, int n) { Vec x(n); for (int i = 0; i < n; ++i) x(i) = a(i); return x; }
+Vec tail(const Vec& a, int n) { Vec x(n); for (int i = 0; i < n; ++i) x(i) = a(a.n - n + i); return x; }
+Vec cat(const Vec& a, const Vec& b) { Vec x(a.n + b.n); for (int i = 0; i < a.n; ++i) x(i) = a(i); for (int i = 0; i < b.n; ++i) x(a.n + i) = b(i); return x; }
+Mat blocks(const Mat& a, const Mat& b, const Mat& c, const Mat& d) {   // vstack(hstack(a, b), hstack(c, d))
+    Mat m(a.r + c.r, a.c + b.c);
+    for (int i = 0; i < a.r; ++i) { for (int j = 0; j < a.c; ++j) m(i, j) = a(i, j); for (int j = 0; j < b.c; ++j) m(i, a.c + j) = b(i, j); }
+    for (int i = 0; i < c.r; ++i) { for (int j = 0; j < c.c; ++j) m(a.r + i, j) = c(i, j); for (int j = 0; j < d.c; ++j) m(a.r + i, c.c + j) = d(i, j); }
+    return m;
+}
+
+struct Gaussian { Vec m; Mat C; };                 // Gaussians.h:24-40
+struct Affine { Vec a; Mat F; Mat A; };            // Gaussians.h:52-69
+struct Separated { Gaussian marginal; Affine conditional; };   // Gaussians.h:91-107
+
+Gaussian gaussian_multiply(const Gaussian& n1, const Gaussian& n2) {   // Gaussians.h:42-49
+    Mat Si = inverse(add(n1.C, n2.C));
+    Gaussian n3;
+    n3.m = add(mul(mul(n2.C, Si), n1.m), mul(mul(n1.C, Si), n2.m));
+    n3.C = mul(mul(n1.C, Si), n2.C);
+    return n3;
+}
+Affine affine_transform(const Affine& g) {   // Gaussians.h:71-81
+    Mat Fi = inverse(g.F);
+    Affine n;
+    n.a = neg(mul(Fi, g.a));
+    n.F = Fi;
+    n.A = mul(mul(Fi, g.A), T(Fi));
+    return n;
+}
+Gaussian affine_transform_at(const Affine& g, const Vec& y) {   // Gaussians.h:83-87
+    Mat Fi = inverse(g.F);
+    Gaussian n;
+    n.m = mul(Fi, sub(y, g.a));
+    n.C = mul(mul(Fi, g.A), T(Fi));
+    return n;
+}
+Gaussian to_joint(const Separated& s) {   // Gaussians.h:109-124
+    Gaussian j;
+    j.m = cat(s.marginal.m, add(s.conditional.a, mul(s.conditional.F, s.marginal.m)));
+    j.C = blocks(s.marginal.C, mul(T(s.marginal.C), T(s.conditional.F)), mul(s.conditional.F, s.marginal.C),
+                 add(s.conditional.A, mul(mul(s.conditional.F, T(s.marginal.C)), T(s.conditional.F))));
+    return j;
+}
+Separated separate_gaussian(const Gaussian& joint) {   // Gaussians.h:127-145
+    const int n = 4;
+    Mat B = block(joint.C, n, n, n, n), K = block(joint.C, 0, n, n, n), A = block(joint.C, 0, 0, n, n);
+    Vec a = head(joint.m, n), b = tail(joint.m, n);
+    Separated s;
+    s.marginal.m = a;
+    s.marginal.C = A;
+    Mat KtAi = mul(T(K), inverse(A));
+    s.conditional.a = sub(b, mul(KtAi, a));
+    s.conditional.F = KtAi;
+    s.conditional.A = sub(B, mul(KtAi, K));
+    return s;
+}
+Gaussian flip_xy(const Gaussian& g) {   // Gaussians.h:147-158
+    const int n = 4;
+    Gaussian r;
+    r.m = cat(tail(g.m, n), head(g.m, n));
+    r.C = blocks(block(g.C, n, n, n, n), T(block(g.C, 0, n, n, n)), T(block(g.C, n, 0, n, n)), block(g.C, 0, 0, n, n));
+    return r;
+}
+
+Gaussian include_measurement(const Gaussian& joint, double D00, double D11, double x, double g) {   // correlation_tree.h:132-154
+    Mat S = block(joint.C, 0, 0, 2, 2);
+    S(0, 0) = S(0, 0) + D00; S(0, 1) = S(0, 1) + 0.0; S(1, 0) = S(1, 0) + 0.0; S(1, 1) = S(1, 1) + D11;
+    Vec xg(2);
+    xg(0) = x - joint.m(0);
+    xg(1) = g - joint.m(1);
+    Mat Si = inverse(S);
+    Mat K = block(joint.C, 0, 0, 2, joint.C.c);
+    Mat KtSi = mul(T(K), Si);
+    Gaussian n;
+    n.m = add(joint.m, mul(KtSi, xg));
+    n.C = sub(joint.C, mul(KtSi, K));
+    return n;
+}
+
+struct StepOut { Vec mean1, mean2; Mat cov1, cov2, cross; };
+
+// the common part of consecutive_joint / consecutive_conditional (correlation_tree.h:325-345, :360-382)
+StepOut step_from_forward(const double* mf, const double* cf, double dt, const double* p) {
+    StepOut o;
+    o.mean1 = vec4(mf);
+    o.cov1 = mat4(cf);
+    double cross[16], m[4], c[16];
+    M::cross_cov_model(mf, cf, dt, p, cross);
+    std::memcpy(m, mf, sizeof m);
+    std::memcpy(c, cf, sizeof c);
+    M::mean_cov_model(m, c, dt, p);
+    o.cross = mat4(cross);
+    o.mean2 = vec4(m);
+    o.cov2 = mat4(c);
+    return o;
+}
+// the binomial branch shared by consecutive_joint_cell_division / consecutive_conditional_cell_division
+StepOut division_binomial(const double* mf, const double* cf, double dt, const double* p) {   // correlation_tree.h:165-203
+    StepOut o;
+    o.mean1 = vec4(mf);
+    o.cov1 = mat4(cf);
+    double mean[4], cov[16];
+    std::memcpy(mean, mf, sizeof mean);
+    std::memcpy(cov, cf, sizeof cov);
+    M::mean_cov_model(mean, cov, dt, p);
+    double var_dx = p[9], var_dg = p[10];
+    cov[0] += var_dx;
+    cov[1] = cov[4] = mean[1] / 2. * var_dx + cov[1];
+    cov[5] = var_dx * (mean[1] * mean[1] + cov[5]) / 2. + var_dg * mean[1] / 4. * (1 - var_dx) + cov[5] / 4.;
+    cov[9] /= 2; cov[6] /= 2;
+    cov[13] /= 2; cov[7] /= 2;
+    mean[0] = mean[0] + -std::log(2.);
+    mean[1] = 0.5 * mean[1] + 0.0;
+    o.cross = mat4(cf);
+    for (int j = 0; j < 4; ++j) o.cross(1, j) /= 2.;
+    o.mean2 = vec4(mean);
+    o.cov2 = mat4(cov);
+    return o;
+}
+Affine division_gauss_conditional(const double* p) {   // correlation_tree.h:176-179, :224-228, :302-312
+    Affine c;
+    c.F = Mat(4, 4);
+    for (int i = 0; i < 4; ++i) c.F(i, i) = 1.0;
+    c.F(1, 1) = 0.5;
+    c.a = Vec(4);
+    c.a(0) = -std::log(2.);
+    c.A = Mat(4, 4);
+    c.A(0, 0) = p[9];
+    c.A(1, 1) = p[10];
+    return c;
+}
+
+struct JointCtx {
+    const ggp_oracle_forest* f;
+    const double* params;
+    double tol;
+    const double* cell_mean;   // after the backward pass
+    const double *mean_f, *cov_f, *mean_b, *cov_b;
+    long cap, count;
+    long *row, *col;
+    double* rec;
+    long row_ctp;
+    std::vector<Gaussian> cell_joint;   // MOMAdata::joint
+};
+
+Gaussian consecutive_joint(const JointCtx& X, long c, long t, const double* p) {   // correlation_tree.h:325-357
+    long k = X.f->cell_offset[c] + t;
+    StepOut o = step_from_forward(X.mean_f + 4 * k, X.cov_f + 16 * k, X.f->time[k + 1] - X.f->time[k], p);
+    Gaussian j;
+    j.m = cat(o.mean2, o.mean1);
+    j.C = blocks(o.cov2, o.cross, T(o.cross), o.cov1);
+    return j;
+}
+Affine consecutive_conditional(const JointCtx& X, long c, long t, const double* p) {   // correlation_tree.h:360-396
+    long k = X.f->cell_offset[c] + t;
+    StepOut o = step_from_forward(X.mean_f + 4 * k, X.cov_f + 16 * k, X.f->time[k + 1] - X.f->time[k], p);
+    Gaussian j;
+    j.m = cat(o.mean1, o.mean2);
+    j.C = blocks(o.cov1, T(o.cross), o.cross, o.cov2);
+    return affine_transform(separate_gaussian(j).conditional);
+}
+Gaussian consecutive_joint_cell_division(const JointCtx& X, long c, long t, const double* p) {   // correlation_tree.h:160-238
+    const ggp_oracle_forest* f = X.f;
+    long k = f->cell_offset[c] + t;
+    double dt = f->time[f->cell_offset[f->daughter1[c]]] - f->time[k];
+    if (f->division_model == 1) {
+        StepOut o = division_binomial(X.mean_f + 4 * k, X.cov_f + 16 * k, dt, p);
+        Gaussian j;
+        j.m = cat(o.mean2, o.mean1);
+        j.C = blocks(o.cov2, o.cross, T(o.cross), o.cov1);
+        return j;
+    }
+    Separated s;
+    s.marginal.m = vec4(X.mean_f + 4 * k);
+    s.marginal.C = mat4(X.cov_f + 16 * k);
+    s.conditional = division_gauss_conditional(p);
+    return flip_xy(to_joint(s));
+}
+Affine consecutive_conditional_cell_division(const JointCtx& X, long c, long t, const double* p) {   // correlation_tree.h:241-319
+    const ggp_oracle_forest* f = X.f;
+    long k = f->cell_offset[c] + t;
+    double dt = f->time[f->cell_offset[f->daughter1[c]]] - f->time[k];
+    if (f->division_model == 1) {
+        StepOut o = division_binomial(X.mean_f + 4 * k, X.cov_f + 16 * k, dt, p);
+        Gaussian j;
+        j.m = cat(o.mean1, o.mean2);
+        j.C = blocks(o.cov1, T(o.cross), o.cross, o.cov2);
+        return affine_transform(separate_gaussian(j).conditional);
+    }
+    return affine_transform(division_gauss_conditional(p));
+}
+
+Gaussian next_joint(const Gaussian& joint, const Affine& conditional) {   // correlation_tree.h:403-454
+    Separated sep = separate_gaussian(joint);
+    const Gaussian& n1 = sep.marginal;
+    Mat Si = inverse(add(n1.C, conditional.A));
+    Affine NX;
+    NX.a = add(mul(mul(conditional.A, Si), n1.m), mul(mul(n1.C, Si), conditional.a));   // calc_x
+    NX.F = mul(mul(n1.C, Si), conditional.F);                                            // calc_X
+    NX.A = mul(mul(n1.C, Si), conditional.A);                                            // calc_Y
+    Affine G;
+    G.a = conditional.a;
+    G.F = conditional.F;
+    G.A = add(n1.C, conditional.A);
+    Gaussian next_marginal = affine_transform_at(G, n1.m);
+    Affine nc;   // propagation(sep.conditional, NX), correlation_tree.h:418-423
+    nc.a = add(sep.conditional.a, mul(sep.conditional.F, NX.a));
+    nc.F = mul(sep.conditional.F, NX.F);
+    nc.A = add(sep.conditional.A, mul(mul(sep.conditional.F, NX.A), T(sep.conditional.F)));
+    Separated nj;
+    nj.marginal = next_marginal;
+    nj.conditional = nc;
+    return to_joint(nj);
+}
+
+Gaussian incorporate_backward_prob(const Separated& joint, const double* mb, const double* cb, const double* p) {   // correlation_tree.h:457-482
+    double m[4], c[16];
+    std::memcpy(m, mb, sizeof m);
+    std::memcpy(c, cb, sizeof c);
+    divide_by_prior(m, c, p);   // same expressions as predictions.h:446-463
+    Gaussian backward;
+    backward.m = vec4(m);
+    backward.C = mat4(c);
+    Separated nj;
+    nj.marginal = gaussian_multiply(joint.marginal, backward);
+    nj.conditional = joint.conditional;
+    return to_joint(nj);
+}
+
+bool crosscovariance_is_small(const Gaussian& joint, double tolerance) {   // correlation_tree.h:484-493
+    for (int i = 0; i < 4; ++i)
+        for (int j = 4; j < 8; ++j)
+            if (std::abs(joint.C(i, j) / (joint.m(i) * joint.m(j))) > tolerance) return false;
+    return true;
+}
+
+void emit(JointCtx& X, long col, const Gaussian& g) {   // Joint_vector::add, correlation_tree.h:65-75
+    if (X.count < X.cap) {
+        X.row[X.count] = X.row_ctp;
+        X.col[X.count] = col;
+        double* r = X.rec + 44 * X.count;
+        for (int i = 0; i < 8; ++i) r[i] = g.m(i);
+        int q = 8;
+        for (int i = 0; i < 8; ++i) for (int j = i; j < 8; ++j) r[q++] = g.C(i, j);
+    }
+    ++X.count;
+}
+
+bool calc_joint_distributions(JointCtx& X, long c, long n) {   // correlation_tree.h:499-558
+    const ggp_oracle_forest* f = X.f;
+    long o = f->cell_offset[c], T_ = f->cell_offset[c + 1] - o;
+    for (long m = 1; n + m < T_; ++m) {
+        long idx = n + m;
+        const double* p = pv(X.params, f->segment[o + idx]);
+        double D11 = f->noise_model == 1 ? p[8] * (X.cell_mean[4 * c + 1] + f->fp_auto) : p[8];
+        X.cell_joint[c] = include_measurement(X.cell_joint[c], p[7], D11, f->log_length[o + idx], f->fp[o + idx]);
+        Gaussian combined = incorporate_backward_prob(separate_gaussian(X.cell_joint[c]), X.mean_b + 4 * (o + idx), X.cov_b + 16 * (o + idx), p);
+        if (crosscovariance_is_small(combined, X.tol)) return true;
+        emit(X, o + idx, combined);
+        if (idx < T_ - 1) {
+            Affine cond = consecutive_conditional(X, c, idx, p);
+            X.cell_joint[c] = next_joint(X.cell_joint[c], cond);
+        } else {
+            if (f->daughter1[c] >= 0) {
+                Affine cond = consecutive_conditional_cell_division(X, c, idx, pv(X.params, f->segment[o + T_ - 1]));
+                X.cell_joint[c] = next_joint(X.cell_joint[c], cond);
+                X.cell_joint[f->daughter1[c]] = X.cell_joint[c];
+            }
+            if (f->daughter2[c] >= 0) X.cell_joint[f->daughter2[c]] = X.cell_joint[c];
+        }
+    }
+    return false;
+}
+
+void joint_distributions_recr(JointCtx& X, long c, long n, bool is_joint_at_division) {   // correlation_tree.h:566-585
+    if (c < 0) return;
+    if (!is_joint_at_division) {
+        if (calc_joint_distributions(X, c, n)) return;
+    }
+    joint_distributions_recr(X, X.f->daughter1[c], -1, false);
+    joint_distributions_recr(X, X.f->daughter2[c], -1, false);
+}
+
+}  // namespace
+
+extern "C" long ggp_oracle_joints(const ggp_oracle_forest* f, const double* params, int n_seg, double tol,
+                                  const double* cell_mean_after_backward, const double* mean_f, const double* cov_f,
+                                  const double* mean_b, const double* cov_b, long cap, long* row_ctp, long* col_ctp, double* rec44) {
+    // collect_joint_distributions / sc_joint_distributions (correlation_tree.h:588-648)
+    (void)n_seg;
+    JointCtx X{f, params, tol, cell_mean_after_backward, mean_f, cov_f, mean_b, cov_b, cap, 0, row_ctp, col_ctp, rec44, 0, {}};
+    X.cell_joint.resize(f->n_cells);
+    for (long c = 0; c < f->n_cells; ++c) {
+        long o = f->cell_offset[c], T_ = f->cell_offset[c + 1] - o;
+        for (long n = 0; n < T_; ++n) {
+            X.row_ctp = o + n;
+            const double* p = pv(params, f->segment[o + n]);
+            if (n < T_ - 1) {
+                X.cell_joint[c] = consecutive_joint(X, c, n, p);
+                joint_distributions_recr(X, c, n, false);
+            } else {
+                if (f->daughter1[c] >= 0) {
+                    X.cell_joint[c] = consecutive_joint_cell_division(X, c, n, p);
+                    X.cell_joint[f->daughter1[c]] = X.cell_joint[c];
+                }
+                if (f->daughter2[c] >= 0) X.cell_joint[f->daughter2[c]] = X.cell_joint[c];
+                joint_distributions_recr(X, c, n, true);
+            }
+        }
+    }
+    return X.count;
+}

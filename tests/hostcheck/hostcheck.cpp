@@ -36,6 +36,7 @@ void hc_propagate(long n, const double* state14, const double* dt, const double*
 // ------------------------------------------------------------------------------------------------
 #include "../../gfp_gaussian_process_b200/csrc/ggp_layout.hpp"
 #include "../../gfp_gaussian_process_b200/csrc/ggp_cell.cuh"
+#include "../../gfp_gaussian_process_b200/csrc/ggp_joints.cuh"
 
 static GgpDevForest hc_dev(const GgpLayout& L, const ggp_forest_desc* d) {
     GgpDevForest F;
@@ -98,5 +99,32 @@ int hc_predict(const ggp_forest_desc* d, const double* params, int n_seg, double
     for (int64_t s = 0; s < L.n_cells; ++s)
         for (int k = 0; k < 20; ++k) bstate_cells[20 * (int64_t)L.cell_of_slot[s] + k] = bstate[20 * s + k];
     return 0;
+}
+
+// joints on the host: predict, per-ctp preparation, then one walk per start point (row), rows in ctp order;
+// returns the number of joints, writes at most cap (unsorted inside a row: emission order)
+long long hc_joints(const ggp_forest_desc* d, const double* params, int n_seg, double tol, long long cap, long long* row, long long* col, double* rec44) {
+    GgpLayout L;
+    if (!L.build(d).empty() || L.max_seg >= n_seg) return -1;
+    double scratch[GGP_SCRATCH];
+    const GgpScratch S{scratch, 1};
+    const GgpDevForest F = hc_dev(L, d);
+    std::vector<double> state((size_t)14 * L.n_cells), bstate((size_t)20 * L.n_cells), fwd((size_t)20 * L.n_ctp), bwd((size_t)20 * L.n_ctp);
+    GgpFwdArgs A{};
+    A.params = params; A.v_count = 1; A.state = state.data(); A.out_fwd = fwd.data();
+    for (int64_t s = 0; s < L.n_cells; ++s) ggp_cell_forward<true, false>(F, A, (int)s, 0, nullptr, &g_tables, S, nullptr);
+    GgpBwdArgs B{};
+    B.params = params; B.fwd = fwd.data(); B.bwd = bwd.data(); B.bstate = bstate.data();
+    for (int64_t s = L.n_cells - 1; s >= 0; --s) ggp_cell_backward(F, B, (int)s, &g_tables, S);
+    std::vector<double> prep((size_t)GGP_JOINT_PREP * L.n_ctp), stack((size_t)72 * (L.n_gen + 1));
+    std::vector<int32_t> stack_slot(L.n_gen + 1);
+    unsigned long long count = 0;
+    GgpJointArgs J{};
+    J.params = params; J.fwd = fwd.data(); J.bwd = bwd.data(); J.bstate = bstate.data(); J.prep = prep.data();
+    J.ctp_slot = L.ctp_slot.data(); J.tol = tol; J.cap = cap; J.count = &count; J.row_ctp = row; J.col_ctp = col; J.rec44 = rec44;
+    J.stack = stack.data(); J.stack_slot = stack_slot.data(); J.stack_depth = L.n_gen + 1;
+    for (int64_t k = 0; k < L.n_ctp; ++k) ggp_ctp_joint_prep(F, J, k, &g_tables, S);
+    for (int64_t k = 0; k < L.n_ctp; ++k) ggp_start_point_joints(F, J, k, 0);
+    return (long long)count;
 }
 }

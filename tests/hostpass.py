@@ -66,3 +66,20 @@ def host_predict(data, params):
     assert rc == 0
     sp = lambda a: (a[:, :4], a[:, 4:].reshape(-1, 4, 4))
     return {"forward": sp(fwd), "backward": sp(bwd), "prediction": sp(comb), "bstate": sp(bstate)}
+
+
+def host_joints(data, params, tol, cap):
+    """sparse joints from the product's host-compiled code, sorted by (row, col)"""
+    p = np.ascontiguousarray(params, dtype=np.float64).reshape(-1, 11)
+    row = np.zeros(cap, dtype=np.int64)
+    col = np.zeros(cap, dtype=np.int64)
+    rec = np.zeros((cap, 44))
+    d = make_desc(data)
+    hc().hc_joints.restype = C.c_longlong
+    n = hc().hc_joints(C.byref(d), p.ctypes.data_as(_lib.c_double_p), p.shape[0], C.c_double(tol), C.c_longlong(cap),
+                       row.ctypes.data_as(C.POINTER(C.c_longlong)), col.ctypes.data_as(C.POINTER(C.c_longlong)),
+                       rec.ctypes.data_as(_lib.c_double_p))
+    assert n >= 0
+    k = min(n, cap)
+    order = np.lexsort((col[:k], row[:k]))
+    return n, row[:k][order], col[:k][order], rec[:k][order]

@@ -207,3 +207,43 @@ def test_full_size_properties():
     ll_o, pc_o = o.total_loglik(P, per_cell=True)
     assert same_bits(pc[cells], pc_o)
     f.close()
+
+
+@pytest.mark.parametrize("noise,division", [("const", "gauss"), ("scaled", "binomial")])
+def test_joints_match_oracle(noise, division):
+    """-j through the C ABI: every emitted joint P(z_col, z_row | D), 8 means + 36 covariances, against the oracle"""
+    P = ggp.PARAMS_CONST_GAUSS if noise == "const" else ggp.PARAMS_SCALED_BINOMIAL
+    d = ggp.simulate_forest(6, 4, params=P, noise_model=noise, division_model=division, seed=15, pts_range=(4, 8))
+    f = ggp.Forest(d)
+    o = Oracle(d)
+    ggp.prediction_forward_backward(f, [P])
+    o.predictions([P])
+    n, row, col, rec = o.joints(1e-10, 400000)
+    order = np.lexsort((col, row))
+    r, c, mean, cov = ggp.collect_joint_distributions(f, [P], 1e-10)
+    assert len(r) == n and np.array_equal(r, row[order]) and np.array_equal(c, col[order])
+    assert max_rel(mean, rec[order][:, :8]) <= PRED_RTOL
+    assert same_bits(mean, rec[order][:, :8]) and same_bits(cov, rec[order][:, 8:])
+    # a row block gives exactly the rows asked for
+    k0, k1 = d.n_ctp // 3, 2 * d.n_ctp // 3
+    r2, c2, m2, v2 = ggp.collect_joint_distributions(f, [P], 1e-10, row_begin=k0, row_end=k1)
+    sel = (r >= k0) & (r < k1)
+    assert np.array_equal(r2, r[sel]) and np.array_equal(c2, c[sel]) and same_bits(m2, mean[sel])
+    f.close()
+
+
+def test_joints_segments_ragged():
+    d = ragged_forest()
+    P = np.stack([ggp.PARAMS_SCALED_BINOMIAL, ggp.PARAMS_SCALED_BINOMIAL * np.array([1, 1, 1, 2, 1, 1, 1, 1, 1, 1, 1.])])
+    f = ggp.Forest(d)
+    o = Oracle(d)
+    ggp.prediction_forward_backward(f, P)
+    o.predictions(P)
+    n, row, col, rec = o.joints(1e-10, 400000)
+    order = np.lexsort((col, row))
+    r, c, mean, cov = ggp.collect_joint_distributions(f, P, 1e-10)
+    assert len(r) == n and np.array_equal(r, row[order]) and np.array_equal(c, col[order])
+    assert same_bits(mean, rec[order][:, :8]) and same_bits(cov, rec[order][:, 8:])
+    with pytest.raises(Exception):
+        ggp.collect_joint_distributions(f, P * 1.01, 1e-10)   # not the parameters of the prediction
+    f.close()

@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -19,6 +20,7 @@
 #include "../../include/ggp_b200.h"
 #include "ggp_layout.hpp"
 #include "ggp_kernels.cuh"
+#include "ggp_coop_kernels.cuh"
 #include "ggp_joints.cuh"
 
 namespace {
@@ -72,7 +74,9 @@ struct ggp_forest {
     int32_t n_roots = 0, n_gen = 0, max_seg = 0;
     GgpModel model{};
     GgpLayout L;                          // host topology
-    std::vector<int32_t> gen_partial0;    // [n_gen+1] first block partial of each generation
+    std::vector<int32_t> gen_partial0;    // [n_gen+1] first block partial of each generation (32 cells per block)
+    int64_t coop_ng4_min_groups = 4 * 148 * 2;   // launches with at least this many 32-cell groups use 4 groups per block
+    bool legacy_loglik = false;           // GGP_B200_LEGACY_LOGLIK=1: one-thread-per-cell likelihood kernel (A/B measurements)
     // device
     DevBuf<double> time, x, g;
     DevBuf<int32_t> seg, comb_seg;
@@ -111,12 +115,15 @@ int check_handle(const ggp_forest* f) {
 }
 
 int grid_of(int64_t n) { return (int)((n + GGP_BLOCK - 1) / GGP_BLOCK); }
+int grid_of_coop(int64_t n) { return (int)((n + GGP_COOP_CELLS - 1) / GGP_COOP_CELLS); }
 
 // the pass kernels use ~100 kB of dynamic shared memory per block (tables + per-thread scratch): opt in once per device
 cudaError_t opt_in_smem() {
     cudaError_t e = cudaFuncSetAttribute(ggp_forward_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GGP_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(ggp_forward_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GGP_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(ggp_forward_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GGP_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ggp_loglik_coop_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GGP_COOP_SMEM_BYTES(1));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ggp_loglik_coop_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GGP_COOP_SMEM_BYTES(4));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(ggp_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GGP_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(ggp_joint_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GGP_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(ggp_propagate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GGP_SMEM_BYTES);
@@ -159,7 +166,12 @@ int ggp_forest_create(const ggp_forest_desc* d, ggp_forest** out) {
     f->model.fp_auto = d->fp_auto;
     f->gen_partial0.assign(L.n_gen + 1, 0);
     for (int g = 0; g < L.n_gen; ++g)
-        f->gen_partial0[g + 1] = f->gen_partial0[g] + grid_of(L.gen_start[g + 1] - L.gen_start[g]);
+        f->gen_partial0[g + 1] = f->gen_partial0[g] + grid_of_coop(L.gen_start[g + 1] - L.gen_start[g]);
+    {
+        const char* lg = getenv("GGP_B200_LEGACY_LOGLIK");
+        f->legacy_loglik = lg && lg[0] == '1';
+        if (const char* m = getenv("GGP_B200_NG4_MIN")) f->coop_ng4_min_groups = atoll(m);
+    }
 
     cudaStream_t s = nullptr;
     auto up_d = [&](DevBuf<double>& b, const double* h, int64_t n) {
@@ -263,6 +275,8 @@ int enqueue_loglik(ggp_forest* f, const double* d_params, int32_t n_vec, double*
     const GgpDevForest F = f->dev();
     for (int32_t v0 = 0; v0 < n_vec; v0 += (int32_t)chunk) {
         const int32_t vc = (int32_t)std::min<int64_t>(chunk, n_vec - v0);
+        // kernels with 128 cells per block (carry-mode roots, legacy) leave the tail of their generation's partials unwritten
+        if (d_carry || f->legacy_loglik) GGP_CUDA(cudaMemsetAsync(f->w_partial.p, 0, (size_t)vc * n_partial * sizeof(double), f->stream));
         for (int g = 0; g < f->n_gen; ++g) {
             GgpFwdArgs A{};
             A.slot0 = (int)f->L.gen_start[g];
@@ -281,8 +295,12 @@ int enqueue_loglik(ggp_forest* f, const double* d_params, int32_t n_vec, double*
             const int gx = grid_of(A.n_slots);
             if (g == 0 && d_carry)
                 ggp_forward_kernel<false, true><<<dim3(gx, 1), GGP_BLOCK, GGP_SMEM_BYTES, f->stream>>>(F, A);
-            else
+            else if (f->legacy_loglik)
                 ggp_forward_kernel<false, false><<<dim3(gx, vc), GGP_BLOCK, GGP_SMEM_BYTES, f->stream>>>(F, A);
+            else if ((int64_t)grid_of_coop(A.n_slots) * vc >= f->coop_ng4_min_groups)
+                ggp_loglik_coop_kernel<4><<<dim3((grid_of_coop(A.n_slots) + 3) / 4, vc), GGP_COOP_BLOCK(4), GGP_COOP_SMEM_BYTES(4), f->stream>>>(F, A);
+            else
+                ggp_loglik_coop_kernel<1><<<dim3(grid_of_coop(A.n_slots), vc), GGP_COOP_BLOCK(1), GGP_COOP_SMEM_BYTES(1), f->stream>>>(F, A);
             ++f->last_launches;
         }
         ggp_reduce_kernel<<<vc, 256, 0, f->stream>>>(f->w_partial.p, n_partial, d_out + v0);

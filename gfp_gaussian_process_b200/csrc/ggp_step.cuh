@@ -61,7 +61,7 @@ enum {
 #define GGP_BT_T_INIT {0, 1, 0, 1, 0, 1, 0, 1, 2, 0, 1, 2, 1, 2}
 // groups: B index, c index, range (0: [0,t], 1: [t,2t]), highest order, pair at range start, pair at range end,
 // chained (1: shares the t' = t exponentials of the preceding group), first output slot
-struct GgpGroup { signed char b, c, hi, nk, i0, i1, chain, out; };
+struct GgpGroup { unsigned char b, c, hi, nk, i0, i1, chain, out; };
 #define GGP_GROUP_INIT {                                                                         \
     {0, 0, 0, 1, 0, 1, 0, 0},  {1, 0, 0, 2, 2, 3, 0, 2},  {0, 1, 0, 1, 0, 1, 0, 5},  {1, 1, 0, 2, 2, 3, 0, 7},      \
     {0, 2, 0, 1, 0, 1, 0, 0},  {1, 2, 0, 2, 2, 3, 0, 2},  {1, 3, 0, 0, 2, 3, 0, 5},  {2, 3, 0, 0, 4, 5, 0, 6},      \
@@ -69,12 +69,12 @@ struct GgpGroup { signed char b, c, hi, nk, i0, i1, chain, out; };
     {4, 5, 0, 3, 9, 10, 0, 9}, {4, 5, 1, 3, 10, 11, 1, 13}, {3, 6, 1, 1, 7, 8, 0, 17}, {4, 7, 1, 1, 10, 11, 0, 19}, \
     {5, 8, 1, 0, 12, 13, 0, 21}}
 #if defined(__CUDACC__)
-__constant__ signed char ggp_bt_b_dev[14] = GGP_BT_B_INIT;
-__constant__ signed char ggp_bt_t_dev[14] = GGP_BT_T_INIT;
+__constant__ unsigned char ggp_bt_b_dev[14] = GGP_BT_B_INIT;
+__constant__ unsigned char ggp_bt_t_dev[14] = GGP_BT_T_INIT;
 __constant__ GgpGroup ggp_group_dev[17] = GGP_GROUP_INIT;
 #endif
-static const signed char ggp_bt_b_host[14] = GGP_BT_B_INIT;
-static const signed char ggp_bt_t_host[14] = GGP_BT_T_INIT;
+static const unsigned char ggp_bt_b_host[14] = GGP_BT_B_INIT;
+static const unsigned char ggp_bt_t_host[14] = GGP_BT_T_INIT;
 static const GgpGroup ggp_group_host[17] = GGP_GROUP_INIT;
 #if defined(__CUDA_ARCH__)
 #define GGP_BT_B ggp_bt_b_dev

@@ -37,6 +37,7 @@ void hc_propagate(long n, const double* state14, const double* dt, const double*
 #include "../../gfp_gaussian_process_b200/csrc/ggp_layout.hpp"
 #include "../../gfp_gaussian_process_b200/csrc/ggp_cell.cuh"
 #include "../../gfp_gaussian_process_b200/csrc/ggp_joints.cuh"
+#include "../../gfp_gaussian_process_b200/csrc/ggp_coop.cuh"
 
 static GgpDevForest hc_dev(const GgpLayout& L, const ggp_forest_desc* d) {
     GgpDevForest F;
@@ -78,6 +79,70 @@ int hc_loglik(const ggp_forest_desc* d, const double* params, int n_vec, double*
             }
         }
     for (int v = 0; v < n_vec; ++v) nan_rank[v] = nan[v] == ~0ull ? -1 : (long long)nan[v];
+    return 0;
+}
+
+// the likelihood with the cooperative step (ggp_coop.cuh): the four roles of every phase run in sequence over one
+// cell's scratch column, in the order of ggp_loglik_coop_kernel (ggp_coop_kernels.cuh).  fresh mode only.
+int hc_loglik_coop(const ggp_forest_desc* d, const double* params, int n_vec, double* out_cell_ll, long long* nan_rank) {
+    GgpLayout L;
+    if (!L.build(d).empty()) return -1;
+    double scratch[GGP_CS_COUNT];
+    const GgpScratch S{scratch, 1};
+    const GgpDevForest F = hc_dev(L, d);
+    std::vector<double> state((size_t)14 * L.n_cells);
+    for (int v = 0; v < n_vec; ++v) {
+        const double* p = params + 11 * v;
+        unsigned long long nan = ~0ull;
+        const GgpOuParams ou = ggp_ou(p, false);
+        for (int64_t slot = 0; slot < L.n_cells; ++slot) {
+            const int64_t off = F.s_off[slot];
+            const int n = F.s_n[slot], parent = F.s_parent[slot];
+            double own = 0.0;
+            int t = 0;
+            int64_t from = off;
+            if (parent < 0) {
+                double mu[4], C[16];
+                for (int i = 0; i < 16; ++i) C[i] = 0.0;
+                mu[0] = F.init_f[0]; mu[1] = F.init_f[1];
+                C[0] = F.init_f[2];  C[5] = F.init_f[3];
+                mu[2] = p[0]; mu[3] = p[3];
+                C[10] = p[2] / (2. * p[1]);
+                C[15] = p[5] / (2. * p[4]);
+                const GgpMeas m = ggp_measure16(mu, C, F.x[off], F.g[off], p[7], p[8], F.model);
+                const double ll = ggp_log_evidence(m, &g_tables);
+                own = own + ll;
+                if (ll != ll) GGP_NAN_MIN(&nan, F.s_dfs0[slot]);
+                ggp_posterior16(mu, C, m);
+                GgpState s;
+                ggp_state_from16(s, mu, C);
+                for (int k = 0; k < 4; ++k) S[GGP_CS_ST + k] = s.m[k];
+                for (int k = 0; k < 10; ++k) S[GGP_CS_ST + 4 + k] = s.c[k];
+            } else {
+                for (int k = 0; k < 14; ++k) S[GGP_CS_ST + k] = state[k * L.n_cells + parent];
+                t = -1;
+                from = F.s_off[parent] + F.s_n[parent] - 1;
+            }
+            while (t + 1 < n) {
+                const double dt = F.time[off + t + 1] - F.time[from];
+                for (int ph = 0; ph < 4; ++ph)
+                    for (int role = 0; role < GGP_COOP_ROLES; ++role) ggp_coop_run_phase(ph, role, S, ou, dt, &g_tables);
+                const int64_t at = off + t + 1;
+                double ll = 0.0;
+                for (int role = 0; role < GGP_COOP_ROLES; ++role) {
+                    const double r = ggp_coop_ph4(role, S, t < 0, p, F.x[at], F.g[at], F.model, &g_tables);
+                    if (role == 0) ll = r;
+                }
+                ++t;
+                from = at;
+                own = own + ll;
+                if (ll != ll) GGP_NAN_MIN(&nan, F.s_dfs0[slot] + t);
+            }
+            for (int k = 0; k < 14; ++k) state[k * L.n_cells + slot] = S[GGP_CS_ST + k];
+            out_cell_ll[(int64_t)v * L.n_cells + F.s_cell[slot]] = own;
+        }
+        nan_rank[v] = nan == ~0ull ? -1 : (long long)nan;
+    }
     return 0;
 }
 

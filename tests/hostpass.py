@@ -54,6 +54,19 @@ def host_loglik(data, params, carry=None):
     return cell_ll, nan
 
 
+def host_loglik_coop(data, params):
+    """the cooperative (four-role) likelihood step of ggp_coop.cuh run on the host; fresh mode"""
+    p = np.ascontiguousarray(params, dtype=np.float64).reshape(-1, 11)
+    n_vec = p.shape[0]
+    cell_ll = np.zeros((n_vec, data.n_cells))
+    nan = np.zeros(n_vec, dtype=np.int64)
+    d = make_desc(data)
+    rc = hc().hc_loglik_coop(C.byref(d), p.ctypes.data_as(_lib.c_double_p), n_vec, cell_ll.ctypes.data_as(_lib.c_double_p),
+                             nan.ctypes.data_as(C.POINTER(C.c_longlong)))
+    assert rc == 0
+    return cell_ll, nan
+
+
 def host_predict(data, params):
     p = np.ascontiguousarray(params, dtype=np.float64).reshape(-1, 11)
     M = data.n_ctp

@@ -50,5 +50,5 @@ if hi:
     tot_e = sum(v[1] for v in byop.values())
     print(f"-- SASS: {n_inst} instructions in the kernel, {tot_e:.0f} warp-instructions executed, {tot_s:.0f} stall samples")
     print("   opcode      executed    share   stall-sample share")
-    for op, (s, e) in sorted(byop.items(), key=lambda kv: -kv[1][1])[:18]:
+    for op, (s, e) in sorted(byop.items(), key=lambda kv: -kv[1][1])[:40]:
         print(f"   {op:10s} {e:12.0f}  {100 * e / tot_e:5.1f}%   {100 * s / max(tot_s, 1):5.1f}%")

@@ -11,12 +11,26 @@
 // phase behind the same block barriers.  Warp w has role w % 4 (so the four warps of one scheduler run the same
 // role's instruction stream at about the same time: one instruction fetch serves NG groups) and group w / 4.
 //   NG = 1: 128 threads, 4 blocks per SM; finest granularity, used for generations with few cells
+//   NG = 2: 256 threads, 2 blocks per SM
 //   NG = 4: 512 threads, 1 block per SM; 4x fewer instruction-cache fills per cell (the step's hot code is ~75 kB,
 //           over twice the 32 kB L1.5 instruction cache, so every step streams from L2)
 #define GGP_COOP_BLOCK(NG) ((NG) * GGP_COOP_ROLES * 32)
 #define GGP_COOP_SMEM_BYTES(NG) (sizeof(GgpMathTables) + (size_t)(NG) * GGP_CS_COUNT * GGP_COOP_CELLS * sizeof(double))
 
-template <int NG>
+// barrier of one 4-warp group (GS: named barrier 1 + group, the groups of a block drift freely) or of the whole block
+template <bool GS>
+__device__ __forceinline__ void ggp_coop_sync(int group) {
+    if (GS) asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory");
+    else __syncthreads();
+}
+
+// 8-byte asynchronous copy global -> shared (no register holds the value while it is in flight)
+__device__ __forceinline__ void ggp_cp_async8(double* smem_dst, const double* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void ggp_cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <int NG, bool GS, bool STEP_ALIGN = false>
 __global__ void __launch_bounds__(GGP_COOP_BLOCK(NG), 4 / NG) ggp_loglik_coop_kernel(const GgpDevForest F, const GgpFwdArgs A) {
     GgpMathTables& T = *reinterpret_cast<GgpMathTables*>(ggp_smem);
     __shared__ double sp[GGP_NP];
@@ -76,47 +90,57 @@ __global__ void __launch_bounds__(GGP_COOP_BLOCK(NG), 4 / NG) ggp_loglik_coop_ke
         }
     }
     const int steps = active ? n - 1 - t : 0;
-    int max_steps = __reduce_max_sync(0xffffffffu, steps);
-    if (NG > 1) {   // the barriers are block wide: every group runs the block's longest cell
+    int max_steps = __reduce_max_sync(0xffffffffu, steps);   // same value in the group's four warps (same 32 cells)
+    if (NG > 1 && (!GS || STEP_ALIGN)) {   // block-wide barriers: every group runs the block's longest cell
         if (lane == 0) s_steps[warp] = max_steps;
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < NG * GGP_COOP_ROLES; ++i) max_steps = max(max_steps, s_steps[i]);
     }
     const GgpOuParams ou = ggp_ou(p, false);
-    // measurements of the next step are fetched one step ahead (the loads retire behind a whole step of arithmetic)
-    double dt = 0.0, xo = 0.0, go = 0.0;
-    if (steps > 0) {
+    // The measurements of a step (t_to, t_from, x, g) sit in scratch slots GGP_CS_IN + 4 * (step & 1); role 0 fetches
+    // those of the NEXT step with cp.async while the current step computes (the loads retire behind a whole step
+    // of arithmetic and occupy no registers).
+    if (role == 0 && steps > 0) {
         const int64_t at = off + t + 1;
-        dt = F.time[at] - F.time[from];
-        xo = F.x[at];
-        go = F.g[at];
+        S[GGP_CS_IN + 0] = F.time[at];
+        S[GGP_CS_IN + 1] = F.time[from];
+        S[GGP_CS_IN + 2] = F.x[at];
+        S[GGP_CS_IN + 3] = F.g[at];
     }
-    __syncthreads();
+    ggp_coop_sync<GS>(group);
     for (int it = 0; it < max_steps; ++it) {
         const bool live = it < steps;
-        double dt_n = 0.0, xo_n = 0.0, go_n = 0.0;
-        if (it + 1 < steps) {
+        const int in = GGP_CS_IN + 4 * (it & 1);
+        if (GS && STEP_ALIGN) __syncthreads();   // re-align the block's groups once per step (instruction-cache sharing)
+        if (role == 0 && it + 1 < steps) {
             const int64_t at = off + t + 2;
-            dt_n = F.time[at] - F.time[at - 1];
-            xo_n = F.x[at];
-            go_n = F.g[at];
-        }
-#pragma unroll
-        for (int ph = 0; ph < 4; ++ph) {
-            if (live) ggp_coop_run_phase(ph, role, S, ou, dt, &T);
-            __syncthreads();
+            const int nx = GGP_CS_IN + 4 * ((it + 1) & 1);
+            ggp_cp_async8(&S[nx + 0], F.time + at);
+            ggp_cp_async8(&S[nx + 1], F.time + at - 1);
+            ggp_cp_async8(&S[nx + 2], F.x + at);
+            ggp_cp_async8(&S[nx + 3], F.g + at);
         }
         if (live) {
-            const double ll = ggp_coop_ph4(role, S, t < 0, p, xo, go, F.model, &T);
+            const double dt = S[in + 0] - S[in + 1];
+            ggp_coop_run_phase(0, role, S, ou, dt, &T);
+        }
+        ggp_coop_sync<GS>(group);
+#pragma unroll
+        for (int ph = 1; ph < GGP_COOP_PHASES; ++ph) {
+            if (live) ggp_coop_run_phase(ph, role, S, ou, 0.0, &T);
+            ggp_coop_sync<GS>(group);
+        }
+        if (live) {
+            const double ll = ggp_coop_ph3(role, S, t < 0, p, S[in + 2], S[in + 3], F.model, &T);
             ++t;
             if (role == 0) {
                 own = own + ll;
                 if (ll != ll) GGP_NAN_MIN(A.nan_key + A.v0 + v, F.s_dfs0[slot] + t);
             }
         }
-        dt = dt_n; xo = xo_n; go = go_n;
-        __syncthreads();
+        if (role == 0) ggp_cp_async_wait();
+        ggp_coop_sync<GS>(group);
     }
     if (active && (F.s_d1[slot] >= 0 || F.s_d2[slot] >= 0)) {
         for (int k = role; k < 14; k += GGP_COOP_ROLES) A.state[k * vstride + vbase + slot] = S[GGP_CS_ST + k];

@@ -45,6 +45,7 @@ GGP_HD double ggp_w_im_pos(double x, const double* __restrict__ tab) {
 GGP_HD_NOINLINE double ggp_dawson(double x, const GgpMathTables* __restrict__ M) {
     const double spi2 = 0.8862269254527580136490837416705725913990;   // sqrt(pi)/2
     if (x != x) return x;
+    M = GGP_TABLES(M);
     double w = (x >= 0) ? ggp_w_im_pos(x, M->dawson_tab) : -ggp_w_im_pos(-x, M->dawson_tab);
     return spi2 * w;
 }

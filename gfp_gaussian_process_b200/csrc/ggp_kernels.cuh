@@ -22,7 +22,6 @@ __device__ const GgpMathTables g_ggp_tables = GGP_MATH_TABLES_INIT;
 
 // dynamic shared memory of the pass kernels: [math tables][per-thread scratch, GGP_SCRATCH x GGP_BLOCK doubles]
 #define GGP_SMEM_BYTES (sizeof(GgpMathTables) + (size_t)GGP_SCRATCH * GGP_BLOCK * sizeof(double))
-extern __shared__ __align__(16) unsigned char ggp_smem[];
 
 __device__ __forceinline__ GgpScratch ggp_thread_scratch() {
     GgpScratch S;

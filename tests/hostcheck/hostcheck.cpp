@@ -125,12 +125,12 @@ int hc_loglik_coop(const ggp_forest_desc* d, const double* params, int n_vec, do
             }
             while (t + 1 < n) {
                 const double dt = F.time[off + t + 1] - F.time[from];
-                for (int ph = 0; ph < 4; ++ph)
+                for (int ph = 0; ph < GGP_COOP_PHASES; ++ph)
                     for (int role = 0; role < GGP_COOP_ROLES; ++role) ggp_coop_run_phase(ph, role, S, ou, dt, &g_tables);
                 const int64_t at = off + t + 1;
                 double ll = 0.0;
                 for (int role = 0; role < GGP_COOP_ROLES; ++role) {
-                    const double r = ggp_coop_ph4(role, S, t < 0, p, F.x[at], F.g[at], F.model, &g_tables);
+                    const double r = ggp_coop_ph3(role, S, t < 0, p, F.x[at], F.g[at], F.model, &g_tables);
                     if (role == 0) ll = r;
                 }
                 ++t;

@@ -340,7 +340,7 @@ def run_ours(args):
                             "host log-likelihood and NaN record out), wall clock around the host calls"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak,
-                         "traffic": None, "kernel": "ggp_forward_kernel<false,false> (%d launches/step, one per generation)" % forest.n_generations,
+                         "traffic": None, "kernel": "ggp_loglik_coop_kernel (%d launches/step, one per generation)" % forest.n_generations,
                          "kernel_ms_per_step": kern_ms, "flop_per_ctp": F_ALG,
                          "peak_source": "DFMA micro-benchmark run in this process (ggp_fp64_peak); MEASURED_PEAKS.json holds no FP64 figure",
                          "hbm": {"achieved": n_ctp * B_ALG / (kern_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",

@@ -76,7 +76,7 @@ struct ggp_forest {
     GgpLayout L;                          // host topology
     std::vector<int32_t> gen_partial0;    // [n_gen+1] first block partial of each generation (32 cells per block)
     int64_t coop_ng4_min_groups = 4 * 148 * 2;   // launches with at least this many 32-cell groups use 4 groups per block
-    int coop_variant = 3;                 // GGP_B200_COOP_VARIANT (A/B measurements): 0 = 4 groups/block, block barriers; 2 = 2 groups/block; 3 = 4 groups, per-group barriers
+    int coop_variant = 4;                 // GGP_B200_COOP_VARIANT (A/B measurements): 0 = 4 groups/block, block barriers; 2 = 2 groups/block; 3 = 4 groups, per-group barriers
     bool legacy_loglik = false;           // GGP_B200_LEGACY_LOGLIK=1: one-thread-per-cell likelihood kernel (A/B measurements)
     // device
     DevBuf<double> time, x, g;

@@ -23,6 +23,13 @@
 #include "ggp_coop_kernels.cuh"
 #include "ggp_joints.cuh"
 
+// groups per block of the prediction passes: 3 (384 threads, up to 170 registers) keeps their larger per-thread state
+// (segment lookups, output pointers) out of local memory; with 4 groups the 128-register cap spills loop-carried values
+// and, with the L1 carve-out almost entirely shared memory, every reload goes to L2
+#ifndef GGP_PRED_NG
+#define GGP_PRED_NG 3
+#endif
+
 namespace {
 
 thread_local std::string g_err;
@@ -128,6 +135,10 @@ cudaError_t opt_in_smem() {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(ggp_loglik_coop_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GGP_COOP_SMEM_BYTES(4));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(ggp_loglik_coop_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GGP_COOP_SMEM_BYTES(4));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(ggp_loglik_coop_kernel<4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GGP_COOP_SMEM_BYTES(4));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ggp_loglik_coop_kernel<1, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GGP_COOP_SMEM_BYTES(1));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ggp_loglik_coop_kernel<GGP_PRED_NG, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GGP_COOP_SMEM_BYTES(GGP_PRED_NG));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ggp_backward_coop_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GGP_COOP_SMEM_BYTES(1));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ggp_backward_coop_kernel<GGP_PRED_NG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GGP_COOP_SMEM_BYTES(GGP_PRED_NG));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(ggp_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GGP_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(ggp_joint_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GGP_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(ggp_propagate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GGP_SMEM_BYTES);
@@ -427,7 +438,14 @@ int ggp_predict(ggp_forest* f, const double* params, int32_t n_seg, double* out_
         A.v_count = 1;
         A.state = f->w_state.p;
         A.out_fwd = f->fwd.p;
-        ggp_forward_kernel<true, false><<<dim3(grid_of(A.n_slots), 1), GGP_BLOCK, GGP_SMEM_BYTES, s>>>(F, A);
+        A.n_seg = n_seg;
+        const int ng = grid_of_coop(A.n_slots);
+        if (f->legacy_loglik)
+            ggp_forward_kernel<true, false><<<dim3(grid_of(A.n_slots), 1), GGP_BLOCK, GGP_SMEM_BYTES, s>>>(F, A);
+        else if (ng >= f->coop_ng4_min_groups)
+            ggp_loglik_coop_kernel<GGP_PRED_NG, true, true, true><<<dim3((ng + GGP_PRED_NG - 1) / GGP_PRED_NG, 1), GGP_COOP_BLOCK(GGP_PRED_NG), GGP_COOP_SMEM_BYTES(GGP_PRED_NG), s>>>(F, A);
+        else
+            ggp_loglik_coop_kernel<1, false, false, true><<<dim3(ng, 1), GGP_COOP_BLOCK(1), GGP_COOP_SMEM_BYTES(1), s>>>(F, A);
         ++f->last_launches;
     }
     for (int g = f->n_gen - 1; g >= 0; --g) {
@@ -438,7 +456,14 @@ int ggp_predict(ggp_forest* f, const double* params, int32_t n_seg, double* out_
         B.fwd = f->fwd.p;
         B.bwd = f->bwd.p;
         B.bstate = f->bstate.p;
-        ggp_backward_kernel<<<grid_of(B.n_slots), GGP_BLOCK, GGP_SMEM_BYTES, s>>>(F, B);
+        B.n_seg = n_seg;
+        const int ng = grid_of_coop(B.n_slots);
+        if (f->legacy_loglik)
+            ggp_backward_kernel<<<grid_of(B.n_slots), GGP_BLOCK, GGP_SMEM_BYTES, s>>>(F, B);
+        else if (ng >= f->coop_ng4_min_groups)
+            ggp_backward_coop_kernel<GGP_PRED_NG, true><<<(ng + GGP_PRED_NG - 1) / GGP_PRED_NG, GGP_COOP_BLOCK(GGP_PRED_NG), GGP_COOP_SMEM_BYTES(GGP_PRED_NG), s>>>(F, B);
+        else
+            ggp_backward_coop_kernel<1, false><<<ng, GGP_COOP_BLOCK(1), GGP_COOP_SMEM_BYTES(1), s>>>(F, B);
         ++f->last_launches;
     }
     ggp_combine_kernel<<<grid_of(M), GGP_BLOCK, 0, s>>>(M, f->fwd.p, f->bwd.p, f->comb_seg.p, f->pred_params.p, f->comb.p);

@@ -49,6 +49,7 @@ struct GgpFwdArgs {
     double* cell_ll;             // NULL or [n_vec][n_cells] (caller's cell order)
     unsigned long long* nan_key; // [n_vec] min depth-first ctp rank with a NaN term
     double* out_fwd;             // PRED: [n_ctp][20]
+    int n_seg;                   // PRED: number of parameter sets
 };
 
 struct GgpBwdArgs {
@@ -57,6 +58,7 @@ struct GgpBwdArgs {
     const double* fwd;      // [n_ctp][20] forward posteriors (a leaf starts from the stale one at its last point)
     double* bwd;            // [n_ctp][20] out
     double* bstate;         // [n_cells][20] by slot: MOMAdata::mean/cov after the backward pass (sign-flipped frame)
+    int n_seg;              // number of parameter sets
 };
 
 #if defined(__CUDA_ARCH__)

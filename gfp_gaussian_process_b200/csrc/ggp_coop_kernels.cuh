@@ -15,6 +15,7 @@
 //   NG = 4: 512 threads, 1 block per SM; 4x fewer instruction-cache fills per cell (the step's hot code is ~75 kB,
 //           over twice the 32 kB L1.5 instruction cache, so every step streams from L2)
 #define GGP_COOP_BLOCK(NG) ((NG) * GGP_COOP_ROLES * 32)
+#define GGP_COOP_SEG_SMEM 8   // parameter sets (segments) staged in shared memory by the prediction passes
 #define GGP_COOP_SMEM_BYTES(NG) (sizeof(GgpMathTables) + (size_t)(NG) * GGP_CS_COUNT * GGP_COOP_CELLS * sizeof(double))
 
 // barrier of one 4-warp group (GS: named barrier 1 + group, the groups of a block drift freely) or of the whole block
@@ -30,15 +31,21 @@ __device__ __forceinline__ void ggp_cp_async8(double* smem_dst, const double* gm
 }
 __device__ __forceinline__ void ggp_cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-template <int NG, bool GS, bool STEP_ALIGN = false>
-__global__ void __launch_bounds__(GGP_COOP_BLOCK(NG), 4 / NG) ggp_loglik_coop_kernel(const GgpDevForest F, const GgpFwdArgs A) {
+// PRED = false: likelihood (likelihood.h:36-103, one parameter vector per blockIdx.y); PRED = true: prediction_forward
+// (predictions.h:93-150): parameters by segment, the posterior of every point stored to A.out_fwd.
+template <int NG, bool GS, bool STEP_ALIGN = false, bool PRED = false>
+__global__ void __launch_bounds__(GGP_COOP_BLOCK(NG), NG == 1 ? 3 : 4 / NG) ggp_loglik_coop_kernel(const GgpDevForest F, const GgpFwdArgs A) {
     GgpMathTables& T = *reinterpret_cast<GgpMathTables*>(ggp_smem);
-    __shared__ double sp[GGP_NP];
+    __shared__ double sp[GGP_NP * (PRED ? GGP_COOP_SEG_SMEM : 1)];   // LIK: the vector's parameters; PRED: the first parameter sets
     __shared__ int s_steps[NG * GGP_COOP_ROLES];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int role = warp & (GGP_COOP_ROLES - 1), group = warp / GGP_COOP_ROLES;
-    const int v = blockIdx.y;
-    if (threadIdx.x < GGP_NP) sp[threadIdx.x] = A.params[(int64_t)(A.v0 + v) * GGP_NP + threadIdx.x];
+    const int v = PRED ? 0 : blockIdx.y;
+    if (!PRED && threadIdx.x < GGP_NP) sp[threadIdx.x] = A.params[(int64_t)(A.v0 + v) * GGP_NP + threadIdx.x];
+    if (PRED && (int)threadIdx.x < GGP_NP * min(A.n_seg, GGP_COOP_SEG_SMEM)) sp[threadIdx.x] = A.params[threadIdx.x];
+    // parameters of segment s: from shared memory when staged (a per-step pointer chase through global memory otherwise)
+    const bool seg_staged = A.n_seg <= GGP_COOP_SEG_SMEM;
+    auto seg_params = [&](int s) -> const double* { return seg_staged ? sp + GGP_NP * s : A.params + GGP_NP * s; };
     ggp_stage_tables(&T);   // ends with a block barrier
     GgpScratch S;
     S.base = reinterpret_cast<double*>(ggp_smem + sizeof(GgpMathTables)) + (size_t)group * GGP_CS_COUNT * GGP_COOP_CELLS + lane;
@@ -56,10 +63,12 @@ __global__ void __launch_bounds__(GGP_COOP_BLOCK(NG), 4 / NG) ggp_loglik_coop_ke
         parent = F.s_parent[slot];
     }
     const int64_t vstride = (int64_t)A.v_count * F.n_cells, vbase = (int64_t)v * F.n_cells;
-    const double* p = sp;
+    const int seg0 = (PRED && active) ? F.seg[off] : 0;
     double own = 0.0;
     int t = 0;
     int64_t from = off;
+    __syncthreads();   // sp
+    const double* p = PRED ? seg_params(seg0) : sp;
     if (active) {
         if (parent < 0) {
             if (role == 0) {   // root: first update on the full matrix (predictions.h:63-82, likelihood.h:53-69)
@@ -74,8 +83,9 @@ __global__ void __launch_bounds__(GGP_COOP_BLOCK(NG), 4 / NG) ggp_loglik_coop_ke
                 const GgpMeas m = ggp_measure16(mu, C, F.x[off], F.g[off], p[7], p[8], F.model);
                 const double ll = ggp_log_evidence(m, &T);
                 own = own + ll;
-                if (ll != ll) GGP_NAN_MIN(A.nan_key + A.v0 + v, F.s_dfs0[slot]);
+                if (!PRED && ll != ll) GGP_NAN_MIN(A.nan_key + A.v0 + v, F.s_dfs0[slot]);
                 ggp_posterior16(mu, C, m);
+                if (PRED) ggp_store20(A.out_fwd + 20 * off, mu, C);
                 GgpState s;
                 ggp_state_from16(s, mu, C);
 #pragma unroll
@@ -97,7 +107,7 @@ __global__ void __launch_bounds__(GGP_COOP_BLOCK(NG), 4 / NG) ggp_loglik_coop_ke
 #pragma unroll
         for (int i = 0; i < NG * GGP_COOP_ROLES; ++i) max_steps = max(max_steps, s_steps[i]);
     }
-    const GgpOuParams ou = ggp_ou(p, false);
+    const GgpOuParams ou_lik = ggp_ou(sp, false);   // LIK: one parameter vector for the whole block
     // The measurements of a step (t_to, t_from, x, g) sit in scratch slots GGP_CS_IN + 4 * (step & 1); role 0 fetches
     // those of the NEXT step with cp.async while the current step computes (the loads retire behind a whole step
     // of arithmetic and occupy no registers).
@@ -108,11 +118,15 @@ __global__ void __launch_bounds__(GGP_COOP_BLOCK(NG), 4 / NG) ggp_loglik_coop_ke
         S[GGP_CS_IN + 2] = F.x[at];
         S[GGP_CS_IN + 3] = F.g[at];
     }
+    // PRED: segment of the point a step leaves from / arrives at; the next step's is fetched one step ahead
+    int seg_from = (PRED && active) ? F.seg[from] : 0;
+    int seg_at = (PRED && steps > 0) ? F.seg[off + t + 1] : 0;
     ggp_coop_sync<GS>(group);
     for (int it = 0; it < max_steps; ++it) {
         const bool live = it < steps;
         const int in = GGP_CS_IN + 4 * (it & 1);
         if (GS && STEP_ALIGN) __syncthreads();   // re-align the block's groups once per step (instruction-cache sharing)
+        const int seg_next = (PRED && it + 1 < steps) ? F.seg[off + t + 2] : 0;
         if (role == 0 && it + 1 < steps) {
             const int64_t at = off + t + 2;
             const int nx = GGP_CS_IN + 4 * ((it + 1) & 1);
@@ -121,20 +135,29 @@ __global__ void __launch_bounds__(GGP_COOP_BLOCK(NG), 4 / NG) ggp_loglik_coop_ke
             ggp_cp_async8(&S[nx + 2], F.x + at);
             ggp_cp_async8(&S[nx + 3], F.g + at);
         }
+        const double* pt = p;   // parameters of the point the step arrives at
+        if (PRED && live) {
+            p = seg_params(seg_from);
+            pt = seg_params(seg_at);
+        }
         if (live) {
             const double dt = S[in + 0] - S[in + 1];
-            ggp_coop_run_phase(0, role, S, ou, dt, &T);
+            ggp_coop_run_phase(0, role, S, PRED ? ggp_ou(p, false) : ou_lik, dt, &T);
         }
         ggp_coop_sync<GS>(group);
 #pragma unroll
         for (int ph = 1; ph < GGP_COOP_PHASES; ++ph) {
-            if (live) ggp_coop_run_phase(ph, role, S, ou, 0.0, &T);
+            if (live) ggp_coop_run_phase(ph, role, S, PRED ? ggp_ou(p, false) : ou_lik, 0.0, &T);
             ggp_coop_sync<GS>(group);
         }
         if (live) {
-            const double ll = ggp_coop_ph3(role, S, t < 0, p, S[in + 2], S[in + 3], F.model, &T);
+            const double ll = PRED ? ggp_coop_ph3_pred<false>(role, S, t < 0, p, pt, S[in + 2], S[in + 3], F.model, &T, A.out_fwd + 20 * (off + t + 1))
+                                   : ggp_coop_ph3(role, S, t < 0, p, S[in + 2], S[in + 3], F.model, &T);
             ++t;
-            if (role == 0) {
+            from = off + t;
+            seg_from = seg_at;
+            seg_at = seg_next;
+            if (!PRED && role == 0) {
                 own = own + ll;
                 if (ll != ll) GGP_NAN_MIN(A.nan_key + A.v0 + v, F.s_dfs0[slot] + t);
             }
@@ -145,11 +168,145 @@ __global__ void __launch_bounds__(GGP_COOP_BLOCK(NG), 4 / NG) ggp_loglik_coop_ke
     if (active && (F.s_d1[slot] >= 0 || F.s_d2[slot] >= 0)) {
         for (int k = role; k < 14; k += GGP_COOP_ROLES) A.state[k * vstride + vbase + slot] = S[GGP_CS_ST + k];
     }
-    if (role == 0) {
+    if (!PRED && role == 0) {
         if (active && A.cell_ll) A.cell_ll[(int64_t)(A.v0 + v) * F.n_cells + F.s_cell[slot]] = own;
         double bs = own;   // fixed-order reduction over the block's 32 cells
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) bs = bs + __shfl_xor_sync(0xffffffffu, bs, o);
         if (lane == 0 && gidx * GGP_COOP_CELLS < A.n_slots) A.partial[(int64_t)v * A.n_partial + A.partial0 + gidx] = bs;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// prediction_backward (predictions.h:368-444), cells processed from the leaves upward, one launch per generation.
+// Role 0 builds the cell's starting belief (leaf: predictions.h:318-331; mother: both daughters mapped back through
+// division and multiplied, :201-275); the time-reversed steps then run through the same four phases as the forward
+// passes with the sign-flipped parameters (mean_cov_model_r, :191-198).
+// ------------------------------------------------------------------------------------------------
+template <int NG, bool GS>
+__global__ void __launch_bounds__(GGP_COOP_BLOCK(NG), NG == 1 ? 3 : 4 / NG) ggp_backward_coop_kernel(const GgpDevForest F, const GgpBwdArgs A) {
+    GgpMathTables& T = *reinterpret_cast<GgpMathTables*>(ggp_smem);
+    __shared__ int s_steps[NG * GGP_COOP_ROLES];
+    __shared__ double sp[GGP_NP * GGP_COOP_SEG_SMEM];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int role = warp & (GGP_COOP_ROLES - 1), group = warp / GGP_COOP_ROLES;
+    if ((int)threadIdx.x < GGP_NP * min(A.n_seg, GGP_COOP_SEG_SMEM)) sp[threadIdx.x] = A.params[threadIdx.x];
+    const bool seg_staged = A.n_seg <= GGP_COOP_SEG_SMEM;
+    auto seg_params = [&](int s) -> const double* { return seg_staged ? sp + GGP_NP * s : A.params + GGP_NP * s; };
+    ggp_stage_tables(&T);
+    GgpScratch S;
+    S.base = reinterpret_cast<double*>(ggp_smem + sizeof(GgpMathTables)) + (size_t)group * GGP_CS_COUNT * GGP_COOP_CELLS + lane;
+    S.stride = GGP_COOP_CELLS;
+
+    const int gidx = blockIdx.x * NG + group;
+    const int in_gen = gidx * GGP_COOP_CELLS + lane;
+    const bool active = in_gen < A.n_slots;
+    const int slot = A.slot0 + (active ? in_gen : 0);
+    int64_t off = 0, from = 0;
+    int n = 0, t = 0;
+    if (active) {
+        off = F.s_off[slot];
+        n = F.s_n[slot];
+        const int d1 = F.s_d1[slot], d2 = F.s_d2[slot];
+        const bool leaf = d1 < 0 && d2 < 0;
+        const int da = d1 >= 0 ? d1 : d2;
+        t = leaf ? n - 1 : n;                       // mothers start at a virtual point: the daughters' first time
+        from = leaf ? off + t : F.s_off[da];
+        if (role == 0) {
+            const double* p0 = A.params + GGP_NP * F.seg[off + n - 1];
+            double mu[4], C[16], R[16], rm[4];
+            GgpState s;
+            if (leaf) {
+                const double* fs = A.fwd + 20 * from;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) C[i] = fs[4 + i];
+                mu[0] = F.init_r[0]; mu[1] = F.init_r[1];
+                C[0] = F.init_r[2];  C[5] = F.init_r[3];
+                mu[2] = -p0[0]; mu[3] = -p0[3];
+                C[10] = p0[2] / (2. * p0[1]);
+                C[15] = p0[5] / (2. * p0[4]);
+                ggp_reverse_mean(mu, rm);
+                ggp_reverse_cov(C, R);
+                ggp_store20(A.bwd + 20 * from, rm, R);
+                const GgpMeas m = ggp_measure16(mu, C, F.x[from], F.g[from], p0[7], p0[8], F.model);
+                ggp_posterior16(mu, C, m);
+                ggp_state_from16(s, mu, C);
+                if (t == 0) ggp_store20(A.bstate + 20 * (int64_t)slot, mu, C);   // one-point leaf: no step follows
+            } else {
+                const double* b1 = A.bstate + 20 * (int64_t)da;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) mu[i] = b1[i];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) C[i] = b1[4 + i];
+                ggp_divide_r16(mu, C, p0[9], p0[10], F.model);
+                if (d1 >= 0 && d2 >= 0) {
+                    const double* b2 = A.bstate + 20 * (int64_t)d2;
+                    double mu2[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) mu2[i] = b2[i];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) R[i] = b2[4 + i];
+                    ggp_divide_r16(mu2, R, p0[9], p0[10], F.model);
+                    ggp_multiply_gaussian(mu, C, mu2, R);
+                }
+                ggp_state_from16(s, mu, C);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) S[GGP_CS_ST + k] = s.m[k];
+#pragma unroll
+            for (int k = 0; k < 10; ++k) S[GGP_CS_ST + 4 + k] = s.c[k];
+        }
+    }
+    const int steps = active ? t : 0;
+    int max_steps = __reduce_max_sync(0xffffffffu, steps);
+    if (NG > 1) {
+        if (lane == 0) s_steps[warp] = max_steps;
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < NG * GGP_COOP_ROLES; ++i) max_steps = max(max_steps, s_steps[i]);
+    }
+    if (role == 0 && steps > 0) {
+        const int64_t at = off + t - 1;
+        S[GGP_CS_IN + 0] = F.time[from];
+        S[GGP_CS_IN + 1] = F.time[at];
+        S[GGP_CS_IN + 2] = F.x[at];
+        S[GGP_CS_IN + 3] = F.g[at];
+    }
+    int seg_at = steps > 0 ? F.seg[off + t - 1] : 0;
+    ggp_coop_sync<GS>(group);
+    for (int it = 0; it < max_steps; ++it) {
+        const bool live = it < steps;
+        const int in = GGP_CS_IN + 4 * (it & 1);
+        if (GS && NG > 1) __syncthreads();
+        const int64_t at = off + t - 1;   // the point this step arrives at
+        const int seg_next = it + 1 < steps ? F.seg[at - 1] : 0;
+        if (role == 0 && it + 1 < steps) {
+            const int nx = GGP_CS_IN + 4 * ((it + 1) & 1);
+            ggp_cp_async8(&S[nx + 0], F.time + at);
+            ggp_cp_async8(&S[nx + 1], F.time + at - 1);
+            ggp_cp_async8(&S[nx + 2], F.x + at - 1);
+            ggp_cp_async8(&S[nx + 3], F.g + at - 1);
+        }
+        const double* pp = A.params;
+        if (live) {
+            pp = seg_params(seg_at);
+            const double dt = S[in + 0] - S[in + 1];
+            ggp_coop_run_phase(0, role, S, ggp_ou(pp, true), dt, &T);
+        }
+        ggp_coop_sync<GS>(group);
+#pragma unroll
+        for (int ph = 1; ph < GGP_COOP_PHASES; ++ph) {
+            if (live) ggp_coop_run_phase(ph, role, S, ggp_ou(pp, true), 0.0, &T);
+            ggp_coop_sync<GS>(group);
+        }
+        if (live) {
+            ggp_coop_store_reversed(role, S, A.bwd + 20 * at);
+            --t;
+            ggp_coop_ph3_pred<false>(role, S, false, pp, pp, S[in + 2], S[in + 3], F.model, &T,
+                                     t == 0 ? A.bstate + 20 * (int64_t)slot : nullptr);
+            seg_at = seg_next;
+        }
+        if (role == 0) ggp_cp_async_wait();
+        ggp_coop_sync<GS>(group);
     }
 }

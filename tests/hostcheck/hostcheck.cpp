@@ -94,7 +94,6 @@ int hc_loglik_coop(const ggp_forest_desc* d, const double* params, int n_vec, do
     for (int v = 0; v < n_vec; ++v) {
         const double* p = params + 11 * v;
         unsigned long long nan = ~0ull;
-        const GgpOuParams ou = ggp_ou(p, false);
         for (int64_t slot = 0; slot < L.n_cells; ++slot) {
             const int64_t off = F.s_off[slot];
             const int n = F.s_n[slot], parent = F.s_parent[slot];
@@ -126,7 +125,7 @@ int hc_loglik_coop(const ggp_forest_desc* d, const double* params, int n_vec, do
             while (t + 1 < n) {
                 const double dt = F.time[off + t + 1] - F.time[from];
                 for (int ph = 0; ph < GGP_COOP_PHASES; ++ph)
-                    for (int role = 0; role < GGP_COOP_ROLES; ++role) ggp_coop_run_phase(ph, role, S, ou, dt, &g_tables);
+                    for (int role = 0; role < GGP_COOP_ROLES; ++role) ggp_coop_run_phase(ph, role, S, ggp_ou(p, false), dt, &g_tables);
                 const int64_t at = off + t + 1;
                 double ll = 0.0;
                 for (int role = 0; role < GGP_COOP_ROLES; ++role) {

@@ -30,6 +30,9 @@ sys.path.insert(0, ROOT)
 
 F_ALG = 3700.0        # algorithmic FP64 flop per cell-timepoint per directional pass
 B_ALG = 28.0          # algorithmic bytes per cell-timepoint: time, x, g (f64) + segment (i32)
+# dram__bytes_read.sum + dram__bytes_write.sum of the likelihood kernel per cell-timepoint, from the ncu --set full capture
+# of the largest generation's launch (profiles/r01_loglik_coop_v2_gen5_steph.txt: 301.4 MB + 3.6 MB for 6 399 691 ctp)
+DRAM_BYTES_PER_CTP_NCU = (301.379840e6 + 3.602688e6) / 6399691.0
 METRIC = "cell-timepoints/s, FP64 log-likelihood evaluation (loglik evals/s in config)"
 
 
@@ -340,7 +343,9 @@ def run_ours(args):
                             "host log-likelihood and NaN record out), wall clock around the host calls"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak,
-                         "traffic": None, "kernel": "ggp_loglik_coop_kernel (%d launches/step, one per generation)" % forest.n_generations,
+                         "traffic": DRAM_BYTES_PER_CTP_NCU * n_ctp, "traffic_unit": "bytes per step (sum over the step's launches; ncu bytes/ctp of "
+                                                                                    "the largest launch x ctp per step)",
+                         "kernel": "ggp_loglik_coop_kernel (%d launches/step, one per generation)" % forest.n_generations,
                          "kernel_ms_per_step": kern_ms, "flop_per_ctp": F_ALG,
                          "peak_source": "DFMA micro-benchmark run in this process (ggp_fp64_peak); MEASURED_PEAKS.json holds no FP64 figure",
                          "hbm": {"achieved": n_ctp * B_ALG / (kern_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",

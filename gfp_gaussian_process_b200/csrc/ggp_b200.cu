@@ -139,6 +139,7 @@ cudaError_t opt_in_smem() {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(ggp_loglik_coop_kernel<GGP_PRED_NG, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GGP_COOP_SMEM_BYTES(GGP_PRED_NG));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(ggp_backward_coop_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GGP_COOP_SMEM_BYTES(1));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(ggp_backward_coop_kernel<GGP_PRED_NG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GGP_COOP_SMEM_BYTES(GGP_PRED_NG));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ggp_loglik_chain_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GGP_COOP_SMEM_BYTES_CHAIN);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(ggp_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GGP_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(ggp_joint_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GGP_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(ggp_propagate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GGP_SMEM_BYTES);
@@ -292,7 +293,7 @@ int enqueue_loglik(ggp_forest* f, const double* d_params, int32_t n_vec, double*
     for (int32_t v0 = 0; v0 < n_vec; v0 += (int32_t)chunk) {
         const int32_t vc = (int32_t)std::min<int64_t>(chunk, n_vec - v0);
         // kernels with 128 cells per block (carry-mode roots, legacy) leave the tail of their generation's partials unwritten
-        if (d_carry || f->legacy_loglik) GGP_CUDA(cudaMemsetAsync(f->w_partial.p, 0, (size_t)vc * n_partial * sizeof(double), f->stream));
+        if (f->legacy_loglik) GGP_CUDA(cudaMemsetAsync(f->w_partial.p, 0, (size_t)vc * n_partial * sizeof(double), f->stream));
         for (int g = 0; g < f->n_gen; ++g) {
             GgpFwdArgs A{};
             A.slot0 = (int)f->L.gen_start[g];
@@ -309,8 +310,10 @@ int enqueue_loglik(ggp_forest* f, const double* d_params, int32_t n_vec, double*
             A.nan_key = d_nan;
             A.out_fwd = nullptr;
             const int gx = grid_of(A.n_slots);
-            if (g == 0 && d_carry)
+            if (g == 0 && d_carry && f->legacy_loglik)
                 ggp_forward_kernel<false, true><<<dim3(gx, 1), GGP_BLOCK, GGP_SMEM_BYTES, f->stream>>>(F, A);
+            else if (g == 0 && d_carry)
+                ggp_loglik_chain_coop_kernel<<<dim3(grid_of_coop(A.n_slots), 1), GGP_COOP_BLOCK(1), GGP_COOP_SMEM_BYTES_CHAIN, f->stream>>>(F, A);
             else if (f->legacy_loglik)
                 ggp_forward_kernel<false, false><<<dim3(gx, vc), GGP_BLOCK, GGP_SMEM_BYTES, f->stream>>>(F, A);
             else if ((int64_t)grid_of_coop(A.n_slots) * vc >= f->coop_ng4_min_groups) {

@@ -310,3 +310,118 @@ __global__ void __launch_bounds__(GGP_COOP_BLOCK(NG), NG == 1 ? 3 : 4 / NG) ggp_
         ggp_coop_sync<GS>(group);
     }
 }
+
+// ------------------------------------------------------------------------------------------------
+// Carry mode: the reference's roots keep their covariance object across evaluations; only its
+// diagonal is reset (predictions.h:64-78), so evaluation v of a root starts from the off-diagonals evaluation v-1
+// left at the root's last point.  The vectors of a batch therefore form a sequential chain per root: this kernel runs
+// the roots' generation for ALL vectors of the chunk one after the other (32 roots per block, four roles), the other
+// generations use ggp_loglik_coop_kernel with one block column per vector.  A.carry [n_roots][16] in/out.
+// ------------------------------------------------------------------------------------------------
+#define GGP_COOP_SMEM_BYTES_CHAIN (sizeof(GgpMathTables) + (size_t)GGP_CS_COUNT_CHAIN * GGP_COOP_CELLS * sizeof(double))
+
+__global__ void __launch_bounds__(GGP_COOP_BLOCK(1), 3) ggp_loglik_chain_coop_kernel(const GgpDevForest F, const GgpFwdArgs A) {
+    GgpMathTables& T = *reinterpret_cast<GgpMathTables*>(ggp_smem);
+    __shared__ double sp[GGP_NP];
+    const int role = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    ggp_stage_tables(&T);
+    GgpScratch S;
+    S.base = reinterpret_cast<double*>(ggp_smem + sizeof(GgpMathTables)) + lane;
+    S.stride = GGP_COOP_CELLS;
+    const int in_gen = blockIdx.x * GGP_COOP_CELLS + lane;
+    const bool active = in_gen < A.n_slots;
+    const int slot = A.slot0 + (active ? in_gen : 0);
+    int64_t off = 0;
+    int n = 0;
+    if (active) {
+        off = F.s_off[slot];
+        n = F.s_n[slot];
+        for (int i = role; i < 16; i += GGP_COOP_ROLES) S[GGP_CS_CARRY + 4 + i] = A.carry[16 * (int64_t)F.s_root[slot] + i];
+    }
+    const int steps = active ? n - 1 : 0;
+    const int max_steps = __reduce_max_sync(0xffffffffu, steps);
+    const int64_t vstride = (int64_t)A.v_count * F.n_cells;
+    for (int v = 0; v < A.v_count; ++v) {
+        __syncthreads();
+        if (threadIdx.x < GGP_NP) sp[threadIdx.x] = A.params[(int64_t)(A.v0 + v) * GGP_NP + threadIdx.x];
+        __syncthreads();
+        const double* p = sp;
+        const int64_t vbase = (int64_t)v * F.n_cells;
+        double own = 0.0;
+        if (active && role == 0) {   // first update on the full matrix with the stale off-diagonals
+            double mu[4], C[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) C[i] = S[GGP_CS_CARRY + 4 + i];
+            mu[0] = F.init_f[0]; mu[1] = F.init_f[1];
+            C[0] = F.init_f[2];  C[5] = F.init_f[3];
+            mu[2] = p[0]; mu[3] = p[3];
+            C[10] = p[2] / (2. * p[1]);
+            C[15] = p[5] / (2. * p[4]);
+            const GgpMeas m = ggp_measure16(mu, C, F.x[off], F.g[off], p[7], p[8], F.model);
+            const double ll = ggp_log_evidence(m, &T);
+            own = own + ll;
+            if (ll != ll) GGP_NAN_MIN(A.nan_key + A.v0 + v, F.s_dfs0[slot]);
+            ggp_posterior16(mu, C, m);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) S[GGP_CS_CARRY + 4 + i] = C[i];
+            GgpState s;
+            ggp_state_from16(s, mu, C);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) S[GGP_CS_ST + k] = s.m[k];
+#pragma unroll
+            for (int k = 0; k < 10; ++k) S[GGP_CS_ST + 4 + k] = s.c[k];
+            if (steps > 0) {
+                S[GGP_CS_IN + 0] = F.time[off + 1];
+                S[GGP_CS_IN + 1] = F.time[off];
+                S[GGP_CS_IN + 2] = F.x[off + 1];
+                S[GGP_CS_IN + 3] = F.g[off + 1];
+            }
+        }
+        __syncthreads();
+        const GgpOuParams ou = ggp_ou(p, false);
+        for (int it = 0; it < max_steps; ++it) {
+            const bool live = it < steps;
+            const int in = GGP_CS_IN + 4 * (it & 1);
+            if (role == 0 && it + 1 < steps) {
+                const int64_t at = off + it + 2;
+                const int nx = GGP_CS_IN + 4 * ((it + 1) & 1);
+                ggp_cp_async8(&S[nx + 0], F.time + at);
+                ggp_cp_async8(&S[nx + 1], F.time + at - 1);
+                ggp_cp_async8(&S[nx + 2], F.x + at);
+                ggp_cp_async8(&S[nx + 3], F.g + at);
+            }
+            if (live) ggp_coop_run_phase(0, role, S, ou, S[in + 0] - S[in + 1], &T);
+            __syncthreads();
+#pragma unroll
+            for (int ph = 1; ph < GGP_COOP_PHASES; ++ph) {
+                if (live) ggp_coop_run_phase(ph, role, S, ou, 0.0, &T);
+                __syncthreads();
+            }
+            if (live) {
+                const bool last = it + 1 == steps;   // the complete posterior of the last point is what the next vector inherits
+                const double ll = ggp_coop_ph3_out<true>(role, S, false, p, p, S[in + 2], S[in + 3], F.model, &T,
+                                                         GgpOutScratch{S, last ? (int)GGP_CS_CARRY : -1});
+                if (role == 0) {
+                    own = own + ll;
+                    if (ll != ll) GGP_NAN_MIN(A.nan_key + A.v0 + v, F.s_dfs0[slot] + it + 1);
+                }
+            }
+            if (role == 0) ggp_cp_async_wait();
+            __syncthreads();
+        }
+        if (active && (F.s_d1[slot] >= 0 || F.s_d2[slot] >= 0)) {
+            for (int k = role; k < 14; k += GGP_COOP_ROLES) A.state[k * vstride + vbase + slot] = S[GGP_CS_ST + k];
+        }
+        if (role == 0) {
+            if (active && A.cell_ll) A.cell_ll[(int64_t)(A.v0 + v) * F.n_cells + F.s_cell[slot]] = own;
+            double bs = own;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) bs = bs + __shfl_xor_sync(0xffffffffu, bs, o);
+            if (lane == 0) A.partial[(int64_t)v * A.n_partial + A.partial0 + blockIdx.x] = bs;
+        }
+    }
+    __syncthreads();
+    if (active) {
+        for (int i = role; i < 16; i += GGP_COOP_ROLES) A.carry[16 * (int64_t)F.s_root[slot] + i] = S[GGP_CS_CARRY + 4 + i];
+    }
+}

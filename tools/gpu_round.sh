@@ -1,2 +1,3 @@
 set -x
-ncu --set full --clock-control none --import-source on -k regex:ggp_loglik_coop_kernel -s 5 -c 1 -o gpurun_out/prof_r1k_pred -f python tools/measure_configs.py cfg3 > gpurun_out/ncu_cfg3f.log 2>&1
+python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -8 gpurun_out/pytest_gpu.log
+python tools/measure_configs.py cfg1 > gpurun_out/configs_r1d.jsonl 2> gpurun_out/configs_r1d.err; cat gpurun_out/configs_r1d.jsonl; tail -3 gpurun_out/configs_r1d.err

@@ -81,7 +81,14 @@ struct ggp_forest {
     int32_t n_roots = 0, n_gen = 0, max_seg = 0;
     GgpModel model{};
     GgpLayout L;                          // host topology
-    std::vector<int32_t> gen_partial0;    // [n_gen+1] first block partial of each generation (32 cells per block)
+    std::vector<int32_t> gen_partial0;    // [n_gen][n_chunks+1] first block partial of each (generation, upload chunk); 32 cells per partial
+    int32_t n_partial = 0;
+    // streamed upload (ggp_forest_upload_series): chunked copies on their own stream, one event per chunk
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> chunk_ready;
+    cudaEvent_t compute_done = nullptr;
+    bool upload_pending = false;
+    const double* h_inline_params = nullptr;   // set by ggp_loglik for the duration of one streamed evaluation
     int64_t coop_ng4_min_groups = 4 * 148 * 2;   // launches with at least this many 32-cell groups use 4 groups per block
     int coop_variant = 4;                 // GGP_B200_COOP_VARIANT (A/B measurements): 0 = 4 groups/block, block barriers; 2 = 2 groups/block; 3 = 4 groups, per-group barriers
     bool legacy_loglik = false;           // GGP_B200_LEGACY_LOGLIK=1: one-thread-per-cell likelihood kernel (A/B measurements)
@@ -157,7 +164,9 @@ int ggp_forest_create(const ggp_forest_desc* d, ggp_forest** out) {
     if (!d || !out) return fail(GGP_ERR_BAD_ARG, "null argument");
     *out = nullptr;
     ggp_forest* f = new ggp_forest();
-    const std::string why = f->L.build(d);
+    int32_t want_chunks = d->n_ctp >= (int64_t)2000000 ? 3 : 1;   // measured on cfg2: 2 -> 9.7 ms, 3 -> 9.0 ms, 4 -> 9.7 ms, 8 -> 11.7 ms end to end (1 chunk: 11.6 ms)
+    if (const char* m = getenv("GGP_B200_UPLOAD_CHUNKS")) want_chunks = atoi(m);
+    const std::string why = f->L.build(d, want_chunks);
     if (!why.empty()) {
         delete f;
         return fail(GGP_ERR_BAD_ARG, why);
@@ -180,9 +189,17 @@ int ggp_forest_create(const ggp_forest_desc* d, ggp_forest** out) {
     f->model.noise_scaled = d->noise_model == GGP_NOISE_SCALED;
     f->model.division_binomial = d->division_model == GGP_DIVISION_BINOMIAL;
     f->model.fp_auto = d->fp_auto;
-    f->gen_partial0.assign(L.n_gen + 1, 0);
-    for (int g = 0; g < L.n_gen; ++g)
-        f->gen_partial0[g + 1] = f->gen_partial0[g] + grid_of_coop(L.gen_start[g + 1] - L.gen_start[g]);
+    {
+        const int K = L.n_chunks;
+        f->gen_partial0.assign((size_t)L.n_gen * (K + 1), 0);
+        int32_t acc = 0;
+        for (int g = 0; g < L.n_gen; ++g)
+            for (int k = 0; k <= K; ++k) {
+                f->gen_partial0[(size_t)g * (K + 1) + k] = acc;
+                if (k < K) acc += grid_of_coop(L.gen_chunk_start[(size_t)g * (K + 1) + k + 1] - L.gen_chunk_start[(size_t)g * (K + 1) + k]);
+            }
+        f->n_partial = acc;
+    }
     {
         const char* lg = getenv("GGP_B200_LEGACY_LOGLIK");
         f->legacy_loglik = lg && lg[0] == '1';
@@ -211,6 +228,10 @@ int ggp_forest_create(const ggp_forest_desc* d, ggp_forest** out) {
     if (e == cudaSuccess) e = f->s_cell.upload(L.s_cell, s);
     if (e == cudaSuccess) e = f->ctp_slot.upload(L.ctp_slot, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&f->copy_stream, cudaStreamNonBlocking);
+    f->chunk_ready.assign(L.n_chunks, nullptr);
+    for (int k = 0; k < L.n_chunks && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&f->chunk_ready[k], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&f->compute_done, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreate(&f->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&f->ev1);
     if (e != cudaSuccess) {
@@ -234,6 +255,9 @@ void ggp_forest_destroy(ggp_forest* f) {
     f->s_off.release();
     f->s_dfs0.release();
     f->w_nan.release();
+    for (cudaEvent_t ev : f->chunk_ready) if (ev) cudaEventDestroy(ev);
+    if (f->compute_done) cudaEventDestroy(f->compute_done);
+    if (f->copy_stream) cudaStreamDestroy(f->copy_stream);
     if (f->ev0) cudaEventDestroy(f->ev0);
     if (f->ev1) cudaEventDestroy(f->ev1);
     delete f;
@@ -249,10 +273,19 @@ int ggp_forest_upload_series(ggp_forest* f, const double* time, const double* lo
     if (int rc = check_handle(f)) return rc;
     if (!time || !log_length || !fp) return fail(GGP_ERR_BAD_ARG, "null series");
     GGP_CUDA(cudaSetDevice(f->device));
-    const size_t b = f->n_ctp * sizeof(double);
-    GGP_CUDA(cudaMemcpyAsync(f->time.p, time, b, cudaMemcpyHostToDevice, f->stream));
-    GGP_CUDA(cudaMemcpyAsync(f->x.p, log_length, b, cudaMemcpyHostToDevice, f->stream));
-    GGP_CUDA(cudaMemcpyAsync(f->g.p, fp, b, cudaMemcpyHostToDevice, f->stream));
+    // the copies run on their own stream, chunk by chunk, behind whatever the handle's stream still reads; the next
+    // likelihood evaluation starts on a chunk's trees as soon as that chunk has landed (enqueue_loglik)
+    GGP_CUDA(cudaEventRecord(f->compute_done, f->stream));
+    GGP_CUDA(cudaStreamWaitEvent(f->copy_stream, f->compute_done, 0));
+    for (int k = 0; k < f->L.n_chunks; ++k) {
+        const int64_t c0 = f->L.ctp_chunk_start[k];
+        const size_t b = (size_t)(f->L.ctp_chunk_start[k + 1] - c0) * sizeof(double);
+        GGP_CUDA(cudaMemcpyAsync(f->time.p + c0, time + c0, b, cudaMemcpyHostToDevice, f->copy_stream));
+        GGP_CUDA(cudaMemcpyAsync(f->x.p + c0, log_length + c0, b, cudaMemcpyHostToDevice, f->copy_stream));
+        GGP_CUDA(cudaMemcpyAsync(f->g.p + c0, fp + c0, b, cudaMemcpyHostToDevice, f->copy_stream));
+        GGP_CUDA(cudaEventRecord(f->chunk_ready[k], f->copy_stream));
+    }
+    f->upload_pending = true;
     f->have_pred = false;
     f->have_prep = false;
     return GGP_OK;
@@ -279,6 +312,14 @@ int64_t ggp_last_launch_count(const ggp_forest* f) { return f ? f->last_launches
 
 namespace {
 
+// make the handle's stream wait for a pending streamed upload (all chunks)
+int wait_for_upload(ggp_forest* f) {
+    if (!f->upload_pending) return GGP_OK;
+    for (cudaEvent_t ev : f->chunk_ready) GGP_CUDA(cudaStreamWaitEvent(f->stream, ev, 0));
+    f->upload_pending = false;
+    return GGP_OK;
+}
+
 // enqueue the likelihood of vectors [0, n_vec) held in d_params; results to d_out [n_vec]
 int enqueue_loglik(ggp_forest* f, const double* d_params, int32_t n_vec, double* d_carry, double* d_out,
                    double* d_cell_ll, unsigned long long* d_nan) {
@@ -286,53 +327,69 @@ int enqueue_loglik(ggp_forest* f, const double* d_params, int32_t n_vec, double*
     int64_t chunk = std::max<int64_t>(1, f->state_budget_bytes / (N * 14 * (int64_t)sizeof(double)));
     chunk = std::min<int64_t>(chunk, n_vec);
     chunk = std::min<int64_t>(chunk, 65535);
-    const int n_partial = f->gen_partial0[f->n_gen];
+    const int n_partial = f->n_partial;
     GGP_CUDA(f->w_state.ensure((size_t)chunk * N * 14));
     GGP_CUDA(f->w_partial.ensure((size_t)chunk * n_partial));
     const GgpDevForest F = f->dev();
+    const int K = f->L.n_chunks;
+    // a freshly uploaded forest is evaluated chunk by chunk behind the copies (one vector chunk only; carry mode and
+    // multi-chunk batches wait for the whole upload)
+    const bool streamed = f->upload_pending && K > 1 && !d_carry && chunk >= n_vec && !f->legacy_loglik;
+    if (!d_params && (f->legacy_loglik || !f->h_inline_params)) return fail(GGP_ERR_BAD_ARG, "inline parameters without a vector");
+    if (!streamed) if (int rc = wait_for_upload(f)) return rc;
     for (int32_t v0 = 0; v0 < n_vec; v0 += (int32_t)chunk) {
         const int32_t vc = (int32_t)std::min<int64_t>(chunk, n_vec - v0);
-        // kernels with 128 cells per block (carry-mode roots, legacy) leave the tail of their generation's partials unwritten
-        if (f->legacy_loglik) GGP_CUDA(cudaMemsetAsync(f->w_partial.p, 0, (size_t)vc * n_partial * sizeof(double), f->stream));
-        for (int g = 0; g < f->n_gen; ++g) {
-            GgpFwdArgs A{};
-            A.slot0 = (int)f->L.gen_start[g];
-            A.n_slots = (int)(f->L.gen_start[g + 1] - f->L.gen_start[g]);
-            A.params = d_params;
-            A.v0 = v0;
-            A.v_count = vc;
-            A.carry = d_carry;
-            A.state = f->w_state.p;
-            A.partial = f->w_partial.p;
-            A.partial0 = f->gen_partial0[g];
-            A.n_partial = n_partial;
-            A.cell_ll = d_cell_ll;
-            A.nan_key = d_nan;
-            A.out_fwd = nullptr;
-            const int gx = grid_of(A.n_slots);
-            if (g == 0 && d_carry && f->legacy_loglik)
-                ggp_forward_kernel<false, true><<<dim3(gx, 1), GGP_BLOCK, GGP_SMEM_BYTES, f->stream>>>(F, A);
-            else if (g == 0 && d_carry)
-                ggp_loglik_chain_coop_kernel<<<dim3(grid_of_coop(A.n_slots), 1), GGP_COOP_BLOCK(1), GGP_COOP_SMEM_BYTES_CHAIN, f->stream>>>(F, A);
-            else if (f->legacy_loglik)
-                ggp_forward_kernel<false, false><<<dim3(gx, vc), GGP_BLOCK, GGP_SMEM_BYTES, f->stream>>>(F, A);
-            else if ((int64_t)grid_of_coop(A.n_slots) * vc >= f->coop_ng4_min_groups) {
-                const int ng = grid_of_coop(A.n_slots);
-                if (f->coop_variant == 2)
-                    ggp_loglik_coop_kernel<2, false><<<dim3((ng + 1) / 2, vc), GGP_COOP_BLOCK(2), GGP_COOP_SMEM_BYTES(2), f->stream>>>(F, A);
-                else if (f->coop_variant == 4)
-                    ggp_loglik_coop_kernel<4, true, true><<<dim3((ng + 3) / 4, vc), GGP_COOP_BLOCK(4), GGP_COOP_SMEM_BYTES(4), f->stream>>>(F, A);
-                else if (f->coop_variant == 3)
-                    ggp_loglik_coop_kernel<4, true><<<dim3((ng + 3) / 4, vc), GGP_COOP_BLOCK(4), GGP_COOP_SMEM_BYTES(4), f->stream>>>(F, A);
-                else
-                    ggp_loglik_coop_kernel<4, false><<<dim3((ng + 3) / 4, vc), GGP_COOP_BLOCK(4), GGP_COOP_SMEM_BYTES(4), f->stream>>>(F, A);
-            } else
-                ggp_loglik_coop_kernel<1, false><<<dim3(grid_of_coop(A.n_slots), vc), GGP_COOP_BLOCK(1), GGP_COOP_SMEM_BYTES(1), f->stream>>>(F, A);
-            ++f->last_launches;
+        // launches do not write every partial (whole-generation launches pack their groups, 128-cell legacy blocks)
+        {
+            const size_t cnt = (size_t)vc * n_partial;
+            ggp_fill64_kernel<<<(unsigned)std::min<size_t>((cnt + 255) / 256, 1184), 256, 0, f->stream>>>(reinterpret_cast<unsigned long long*>(f->w_partial.p), 0ull, cnt);
+        }
+        for (int k = 0; k < (streamed ? K : 1); ++k) {
+            if (streamed) GGP_CUDA(cudaStreamWaitEvent(f->stream, f->chunk_ready[k], 0));
+            for (int g = 0; g < f->n_gen; ++g) {
+                const int64_t* row = f->L.gen_chunk_start.data() + (size_t)g * (K + 1);
+                GgpFwdArgs A{};
+                A.slot0 = (int)(streamed ? row[k] : row[0]);
+                A.n_slots = (int)((streamed ? row[k + 1] : row[K]) - A.slot0);
+                if (A.n_slots == 0) continue;
+                A.params = d_params;
+                if (!d_params) std::memcpy(A.inline_params, f->h_inline_params, (size_t)n_vec * GGP_NP * sizeof(double));
+                A.v0 = v0;
+                A.v_count = vc;
+                A.carry = d_carry;
+                A.state = f->w_state.p;
+                A.partial = f->w_partial.p;
+                A.partial0 = f->gen_partial0[(size_t)g * (K + 1) + (streamed ? k : 0)];
+                A.n_partial = n_partial;
+                A.cell_ll = d_cell_ll;
+                A.nan_key = d_nan;
+                A.out_fwd = nullptr;
+                const int gx = grid_of(A.n_slots);
+                if (g == 0 && d_carry && f->legacy_loglik)
+                    ggp_forward_kernel<false, true><<<dim3(gx, 1), GGP_BLOCK, GGP_SMEM_BYTES, f->stream>>>(F, A);
+                else if (g == 0 && d_carry)
+                    ggp_loglik_chain_coop_kernel<<<dim3(grid_of_coop(A.n_slots), 1), GGP_COOP_BLOCK(1), GGP_COOP_SMEM_BYTES_CHAIN, f->stream>>>(F, A);
+                else if (f->legacy_loglik)
+                    ggp_forward_kernel<false, false><<<dim3(gx, vc), GGP_BLOCK, GGP_SMEM_BYTES, f->stream>>>(F, A);
+                else if ((int64_t)grid_of_coop(A.n_slots) * vc >= f->coop_ng4_min_groups) {
+                    const int ng = grid_of_coop(A.n_slots);
+                    if (f->coop_variant == 2)
+                        ggp_loglik_coop_kernel<2, false><<<dim3((ng + 1) / 2, vc), GGP_COOP_BLOCK(2), GGP_COOP_SMEM_BYTES(2), f->stream>>>(F, A);
+                    else if (f->coop_variant == 4)
+                        ggp_loglik_coop_kernel<4, true, true><<<dim3((ng + 3) / 4, vc), GGP_COOP_BLOCK(4), GGP_COOP_SMEM_BYTES(4), f->stream>>>(F, A);
+                    else if (f->coop_variant == 3)
+                        ggp_loglik_coop_kernel<4, true><<<dim3((ng + 3) / 4, vc), GGP_COOP_BLOCK(4), GGP_COOP_SMEM_BYTES(4), f->stream>>>(F, A);
+                    else
+                        ggp_loglik_coop_kernel<4, false><<<dim3((ng + 3) / 4, vc), GGP_COOP_BLOCK(4), GGP_COOP_SMEM_BYTES(4), f->stream>>>(F, A);
+                } else
+                    ggp_loglik_coop_kernel<1, false><<<dim3(grid_of_coop(A.n_slots), vc), GGP_COOP_BLOCK(1), GGP_COOP_SMEM_BYTES(1), f->stream>>>(F, A);
+                ++f->last_launches;
+            }
         }
         ggp_reduce_kernel<<<vc, 256, 0, f->stream>>>(f->w_partial.p, n_partial, d_out + v0);
         ++f->last_launches;
     }
+    if (streamed) f->upload_pending = false;
     GGP_CUDA(cudaGetLastError());
     return GGP_OK;
 }
@@ -355,11 +412,20 @@ int ggp_loglik(ggp_forest* f, const double* params, int32_t n_vec, double* root_
         GGP_CUDA(f->w_carry.ensure((size_t)f->n_roots * 16));
         GGP_CUDA(cudaMemcpyAsync(f->w_carry.p, root_carry, (size_t)f->n_roots * 16 * sizeof(double), cudaMemcpyHostToDevice, s));
     }
-    GGP_CUDA(cudaMemcpyAsync(f->w_params.p, params, (size_t)n_vec * GGP_NP * sizeof(double), cudaMemcpyHostToDevice, s));
-    GGP_CUDA(cudaMemsetAsync(f->w_nan.p, 0xff, (size_t)n_vec * sizeof(unsigned long long), s));
+    // behind a streamed upload a DMA copy of the parameters would queue after the whole upload in the host-to-device
+    // copy engine: small batches travel in the launch arguments instead
+    const double* d_params = f->w_params.p;
+    f->h_inline_params = nullptr;
+    if (n_vec <= GGP_INLINE_VECS && f->upload_pending && !root_carry) {
+        f->h_inline_params = params;
+        d_params = nullptr;
+    } else {
+        GGP_CUDA(cudaMemcpyAsync(f->w_params.p, params, (size_t)n_vec * GGP_NP * sizeof(double), cudaMemcpyHostToDevice, s));
+    }
+    ggp_fill64_kernel<<<(unsigned)std::min<size_t>(((size_t)n_vec + 255) / 256, 1184), 256, 0, s>>>(f->w_nan.p, ~0ull, (size_t)n_vec);
     f->last_launches = 0;
     GGP_CUDA(cudaEventRecord(f->ev0, s));
-    if (int rc = enqueue_loglik(f, f->w_params.p, n_vec, root_carry ? f->w_carry.p : nullptr, f->w_out.p,
+    if (int rc = enqueue_loglik(f, d_params, n_vec, root_carry ? f->w_carry.p : nullptr, f->w_out.p,
                                 out_cell_ll ? f->w_cell_ll.p : nullptr, f->w_nan.p))
         return rc;
     GGP_CUDA(cudaEventRecord(f->ev1, s));
@@ -392,7 +458,7 @@ int ggp_loglik_device(ggp_forest* f, const double* d_params, int32_t n_vec, doub
     if (!d_params || !d_out_loglik || n_vec <= 0) return fail(GGP_ERR_BAD_ARG, "bad params/out/n_vec");
     GGP_CUDA(cudaSetDevice(f->device));
     GGP_CUDA(f->w_nan.ensure(n_vec));
-    GGP_CUDA(cudaMemsetAsync(f->w_nan.p, 0xff, (size_t)n_vec * sizeof(unsigned long long), f->stream));
+    ggp_fill64_kernel<<<(unsigned)std::min<size_t>(((size_t)n_vec + 255) / 256, 1184), 256, 0, f->stream>>>(f->w_nan.p, ~0ull, (size_t)n_vec);
     f->last_launches = 0;
     GGP_CUDA(cudaEventRecord(f->ev0, f->stream));
     if (int rc = enqueue_loglik(f, d_params, n_vec, nullptr, d_out_loglik, nullptr, f->w_nan.p)) return rc;
@@ -426,6 +492,7 @@ int ggp_predict(ggp_forest* f, const double* params, int32_t n_seg, double* out_
     GGP_CUDA(f->comb.ensure((size_t)M * 20));
     GGP_CUDA(f->bstate.ensure((size_t)N * 20));
     GGP_CUDA(cudaMemcpyAsync(f->pred_params.p, params, (size_t)n_seg * GGP_NP * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (int rc = wait_for_upload(f)) return rc;
     f->pred_n_seg = n_seg;
     f->have_pred = false;
     f->have_prep = false;

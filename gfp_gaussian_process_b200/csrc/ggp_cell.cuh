@@ -17,6 +17,7 @@
 #include "ggp_linalg.cuh"
 
 #define GGP_NP 11
+#define GGP_INLINE_VECS 8
 
 struct GgpDevForest {
     int64_t n_cells, n_ctp;
@@ -50,6 +51,9 @@ struct GgpFwdArgs {
     unsigned long long* nan_key; // [n_vec] min depth-first ctp rank with a NaN term
     double* out_fwd;             // PRED: [n_ctp][20]
     int n_seg;                   // PRED: number of parameter sets
+    // LIK, params == nullptr: up to GGP_INLINE_VECS parameter vectors travel in the launch arguments (an evaluation that
+    // runs behind a streamed upload must not queue a copy, or read host memory, behind the upload's DMA traffic)
+    double inline_params[GGP_INLINE_VECS * GGP_NP];
 };
 
 struct GgpBwdArgs {

@@ -41,7 +41,8 @@ __global__ void __launch_bounds__(GGP_COOP_BLOCK(NG), NG == 1 ? 3 : 4 / NG) ggp_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int role = warp & (GGP_COOP_ROLES - 1), group = warp / GGP_COOP_ROLES;
     const int v = PRED ? 0 : blockIdx.y;
-    if (!PRED && threadIdx.x < GGP_NP) sp[threadIdx.x] = A.params[(int64_t)(A.v0 + v) * GGP_NP + threadIdx.x];
+    if (!PRED && threadIdx.x < GGP_NP)
+        sp[threadIdx.x] = A.params ? A.params[(int64_t)(A.v0 + v) * GGP_NP + threadIdx.x] : A.inline_params[(A.v0 + v) * GGP_NP + threadIdx.x];
     if (PRED && (int)threadIdx.x < GGP_NP * min(A.n_seg, GGP_COOP_SEG_SMEM)) sp[threadIdx.x] = A.params[threadIdx.x];
     // parameters of segment s: from shared memory when staged (a per-step pointer chase through global memory otherwise)
     const bool seg_staged = A.n_seg <= GGP_COOP_SEG_SMEM;

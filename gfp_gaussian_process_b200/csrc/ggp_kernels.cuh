@@ -90,6 +90,11 @@ __global__ void __launch_bounds__(GGP_BLOCK) ggp_forward_kernel(const GgpDevFore
     }
 }
 
+// 64-bit fill (cudaMemsetAsync may be routed through a copy engine and queue behind a streamed upload)
+__global__ void __launch_bounds__(256) ggp_fill64_kernel(unsigned long long* __restrict__ p, unsigned long long v, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) p[i] = v;
+}
+
 // one value per vector from the per-block partials, fixed order
 __global__ void __launch_bounds__(256) ggp_reduce_kernel(const double* __restrict__ partial, int n_partial,
                                                          double* __restrict__ out) {

@@ -18,6 +18,12 @@ struct GgpLayout {
     int64_t n_cells = 0, n_ctp = 0;
     int32_t n_roots = 0, n_gen = 0, max_seg = 0;
     std::vector<int64_t> gen_start;          // [n_gen+1] slot ranges
+    // streamed upload: the series are cut into n_chunks contiguous ctp ranges; a tree belongs to the chunk its last
+    // point arrives with, and inside a generation the slots are grouped by chunk, so a chunk's trees can be evaluated
+    // (all generations) as soon as that chunk has landed on the device
+    int32_t n_chunks = 1;
+    std::vector<int64_t> ctp_chunk_start;    // [n_chunks+1]
+    std::vector<int64_t> gen_chunk_start;    // [n_gen][n_chunks+1] slot ranges
     std::vector<int32_t> slot_of_cell, cell_of_slot;
     std::vector<int32_t> dfs_cells;          // cells in the reference's depth-first order
     std::vector<int64_t> dfs_ctp0;           // [n_cells+1] by dfs position
@@ -55,7 +61,7 @@ struct GgpLayout {
     }
 
     // returns "" on success, else the reason (the reference throws std::invalid_argument)
-    std::string build(const ggp_forest_desc* d) {
+    std::string build(const ggp_forest_desc* d, int32_t want_chunks = 1) {
         if (!d) return "null descriptor";
         if (d->n_cells <= 0 || d->n_ctp <= 0 || !d->cell_offset || !d->parent || !d->time || !d->log_length || !d->fp)
             return "empty forest or missing array";
@@ -108,11 +114,30 @@ struct GgpLayout {
             if (p >= 0 && d1[p] != c && d2[p] != c) return "cell has a parent but is not one of its two daughters";
         }
         n_gen = *std::max_element(gen.begin(), gen.end()) + 1;
-        // slots: by generation, then by number of points (descending), then cell index
+        // upload chunks and the chunk of every cell (= of its tree)
+        n_chunks = std::max<int32_t>(1, std::min<int64_t>(want_chunks, d->n_ctp));
+        ctp_chunk_start.assign(n_chunks + 1, 0);
+        for (int32_t k = 0; k <= n_chunks; ++k) ctp_chunk_start[k] = d->n_ctp * k / n_chunks;
+        std::vector<int32_t> chunk(N, 0);
+        if (n_chunks > 1) {
+            std::vector<int32_t> root_of(N, -1), order(N);
+            std::iota(order.begin(), order.end(), 0);
+            std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return gen[a] < gen[b]; });
+            std::vector<int32_t> tree_chunk(N, 0);
+            for (int32_t c : order) {   // parents before daughters
+                root_of[c] = d->parent[c] < 0 ? c : root_of[d->parent[c]];
+                const int64_t last = d->cell_offset[c + 1] - 1;
+                const int32_t k = (int32_t)(std::upper_bound(ctp_chunk_start.begin(), ctp_chunk_start.end(), last) - ctp_chunk_start.begin()) - 1;
+                tree_chunk[root_of[c]] = std::max(tree_chunk[root_of[c]], k);
+            }
+            for (int64_t c = 0; c < N; ++c) chunk[c] = tree_chunk[root_of[c]];
+        }
+        // slots: by generation, then upload chunk, then number of points (descending), then cell index
         cell_of_slot.resize(N);
         std::iota(cell_of_slot.begin(), cell_of_slot.end(), 0);
         std::stable_sort(cell_of_slot.begin(), cell_of_slot.end(), [&](int32_t a, int32_t b) {
             if (gen[a] != gen[b]) return gen[a] < gen[b];
+            if (chunk[a] != chunk[b]) return chunk[a] < chunk[b];
             const int64_t na = d->cell_offset[a + 1] - d->cell_offset[a], nb = d->cell_offset[b + 1] - d->cell_offset[b];
             if (na != nb) return na > nb;
             return a < b;
@@ -122,6 +147,13 @@ struct GgpLayout {
         gen_start.assign(n_gen + 1, 0);
         for (int64_t c = 0; c < N; ++c) gen_start[gen[c] + 1]++;
         for (int g = 0; g < n_gen; ++g) gen_start[g + 1] += gen_start[g];
+        gen_chunk_start.assign((size_t)n_gen * (n_chunks + 1), 0);
+        for (int64_t c = 0; c < N; ++c) gen_chunk_start[(size_t)gen[c] * (n_chunks + 1) + chunk[c] + 1]++;
+        for (int g = 0; g < n_gen; ++g) {
+            int64_t* row = gen_chunk_start.data() + (size_t)g * (n_chunks + 1);
+            row[0] = gen_start[g];
+            for (int k = 0; k < n_chunks; ++k) row[k + 1] += row[k];
+        }
         // depth-first order of the reference (roots in cell order; cell, daughter1 subtree, daughter2 subtree)
         std::vector<int64_t> dfs0_of_cell(N, 0);
         {

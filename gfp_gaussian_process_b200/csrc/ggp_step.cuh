@@ -358,7 +358,7 @@ GGP_HD void ggp_propagate_impl(GgpState& s, double t, const GgpOuParams& p, cons
         const GgpInts<1> jW_d2 = ggp_load_ints<1>(S, 17);
         const GgpInts<1> jWm_d3 = ggp_load_ints<1>(S, 19);
         const GgpInts<0> jWp_d4 = ggp_load_ints<0>(S, 21);
-        const double mq2 = mq * mq, bq2 = bq * bq, Cxq2 = Cxq * Cxq, Clq2 = Clq * Clq, gq2 = gq * gq;
+        const double mq2 = mq * mq, bq2 = bq * bq, Cxq2 = Cxq * Cxq, Clq2 = Clq * Clq;
         n_gg =
             ((bg * bg) + Cgg) / e2bt
             + 2 * Cgl * mq * jB_c2.I[1]

@@ -78,8 +78,10 @@ int64_t ggp_forest_n_ctp(const ggp_forest* f);
 int64_t ggp_forest_n_roots(const ggp_forest* f);
 int64_t ggp_forest_n_generations(const ggp_forest* f);
 /* replace the measurement arrays (MOMAdata::time/log_length/fp, [n_ctp] each, same topology) from host memory;
- * the copies are asynchronous on the handle's stream when the source is pinned.  Used when the same genealogy
- * is evaluated on new measurements (and by bench.py's end-to-end leg). */
+ * the copies are chunked and asynchronous on an internal copy stream when the source is pinned, and the next ggp_loglik
+ * starts on a chunk's trees as soon as that chunk has landed (the caller must keep the host arrays alive until that call
+ * returns).  The init_cells statistics keep the values of ggp_forest_create.  Used when the same genealogy is evaluated on
+ * new measurements (and by bench.py's end-to-end leg). */
 int ggp_forest_upload_series(ggp_forest* f, const double* time, const double* log_length, const double* fp);
 int ggp_forest_get_init(const ggp_forest* f, double* init_f4, double* init_r4);
 

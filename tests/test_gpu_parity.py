@@ -247,3 +247,41 @@ def test_joints_segments_ragged():
     with pytest.raises(Exception):
         ggp.collect_joint_distributions(f, P * 1.01, 1e-10)   # not the parameters of the prediction
     f.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("chunks", [1, 3, 7])
+def test_streamed_upload_evaluates_chunk_by_chunk(chunks, monkeypatch):
+    """ggp_forest_upload_series cuts the series into chunks; the next evaluation runs a chunk's trees as soon as the chunk
+    has landed.  Same per-cell sums as a forest created from the new series directly, whatever the chunking; also with
+    parents stored after daughters and one-point cells (ragged forest)."""
+    monkeypatch.setenv("GGP_B200_UPLOAD_CHUNKS", str(chunks))
+    for d, P in ((ggp.simulate_forest(40, 4, seed=31), ggp.PARAMS_CONST_GAUSS), (ragged_forest(), ggp.PARAMS_SCALED_BINOMIAL)):
+        f = ggp.Forest(d)
+        ll0, pc0 = ggp.total_likelihood(P, f, per_cell=True)
+        # new measurements on the same genealogy
+        rng = np.random.default_rng(5)
+        x2 = d.log_length + rng.normal(0, 1e-3, d.n_ctp)
+        g2 = d.fp * (1 + rng.normal(0, 1e-3, d.n_ctp))
+        t2 = d.time.copy()
+        f.upload_series(t2.ctypes.data, x2.ctypes.data, g2.ctypes.data)
+        vecs = np.stack([P, P * 1.01])
+        ll1, pc1 = ggp.total_likelihood(vecs, f, per_cell=True)
+        d2 = ggp.LineageData(cell_offset=d.cell_offset, parent=d.parent, time=t2, log_length=x2, fp=g2, segment=d.segment,
+                             noise_model=d.noise_model, division_model=d.division_model, fp_auto=d.fp_auto,
+                             init_f=f.init_stats()[0], init_r=f.init_stats()[1])
+        o = Oracle(d2)
+        for i in range(2):
+            assert same_bits(pc1[i], o.total_loglik(vecs[i], per_cell=True)[1])
+        assert not same_bits(pc1[0], pc0)
+        # and again resident (no upload pending): same numbers
+        ll2, pc2 = ggp.total_likelihood(vecs, f, per_cell=True)
+        # (per-cell sums are identical; the forest total is reduced over different block partials, last-bit differences)
+        assert same_bits(pc2, pc1) and max_rel(ll2, ll1) < 1e-14
+        # predictions after an upload wait for all chunks
+        f.upload_series(d.time.ctypes.data, d.log_length.ctypes.data, d.fp.ctypes.data)
+        pr = ggp.prediction_forward_backward(f, [P] * (int(d.segment.max()) + 1))
+        d.init_f, d.init_r = f.init_stats()
+        ref = Oracle(d).predictions([P] * (int(d.segment.max()) + 1))
+        assert same_bits(pr["prediction"][0], ref["prediction"][0])
+        f.close()

@@ -1,3 +1,6 @@
 set -x
-python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -8 gpurun_out/pytest_gpu.log
-python tools/measure_configs.py cfg1 > gpurun_out/configs_r1d.jsonl 2> gpurun_out/configs_r1d.err; cat gpurun_out/configs_r1d.jsonl; tail -3 gpurun_out/configs_r1d.err
+for k in 2 3 4 6; do GGP_B200_UPLOAD_CHUNKS=$k python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_k$k.json 2>&1; done
+python -c "
+import json
+for k in (2,3,4,6):
+    j=json.load(open('gpurun_out/bench_k%d.json'%k)); print(k, j['ms_per_step'], j['e2e']['ms_per_step'], j['e2e']['value'])"

@@ -143,7 +143,7 @@ def run_reference(args):
     cores = min(host_cores(), 64)
     trees_per_proc = 120          # ~150 k ctp, ~1 s per process per step
     data = ggp.simulate_forest(cores * trees_per_proc, args.generations, seed=20261018)
-    steps, warmup = min(args.steps, 5), min(args.warmup, 1)
+    steps, warmup = min(args.steps, 20), min(args.warmup, 3)   # ~1 s per step on the sample below
     v, ctp, ll, t = cpu_pool_bench(data, ggp.PARAMS_CONST_GAUSS, cores, trees_per_proc, steps, warmup, use_ref)
     kind = "reference" if use_ref else "port"
     sample = ("%d trees x %d generations (%d ctp) of the configs[1] forest per step, %d processes x %d trees; %s"

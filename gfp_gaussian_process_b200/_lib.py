@@ -54,6 +54,7 @@ SIGNATURES = {
     "ggp_forest_n_roots": (C.c_int64, [C.c_void_p]),
     "ggp_forest_n_generations": (C.c_int64, [C.c_void_p]),
     "ggp_forest_get_init": (C.c_int, [C.c_void_p, c_double_p, c_double_p]),
+    "ggp_init_stats": (C.c_int, [C.POINTER(ForestDesc), c_double_p, c_double_p]),
     "ggp_loglik": (C.c_int, [C.c_void_p, c_double_p, C.c_int32, c_double_p, c_double_p, c_double_p, C.POINTER(NanInfo)]),
     "ggp_loglik_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "ggp_sync_kernel_ms": (C.c_int, [C.c_void_p, c_double_p]),

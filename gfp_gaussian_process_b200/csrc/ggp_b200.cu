@@ -305,6 +305,12 @@ int ggp_forest_get_init(const ggp_forest* f, double* init_f4, double* init_r4) {
     return GGP_OK;
 }
 
+int ggp_init_stats(const ggp_forest_desc* d, double* init_f4, double* init_r4) {
+    if (!d || !init_f4 || !init_r4 || d->n_cells <= 0 || !d->cell_offset || !d->log_length || !d->fp) return fail(GGP_ERR_BAD_ARG, "null argument");
+    GgpLayout::init_stats(d, init_f4, init_r4);
+    return GGP_OK;
+}
+
 double ggp_last_kernel_ms(const ggp_forest* f) { return f ? f->last_ms : -1.0; }
 int64_t ggp_last_launch_count(const ggp_forest* f) { return f ? f->last_launches : -1; }
 

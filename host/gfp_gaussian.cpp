@@ -13,7 +13,8 @@
 //     batched launches; results are those of one-by-one evaluation (the library chains the reference's history
 //     dependence, SURVEY.md H3, through `root_carry` in evaluation order);
 //   * NLopt is replaced by ggp_neldermead.hpp (iterate parity unpinned);
-//   * extra options: --device N, --fresh (every evaluation starts from zero root off-diagonals, i.e. is a pure
+//   * extra options: --device N, --devices a,b,.. (lineage trees sharded over several GPUs, one host thread and one
+//     forest handle each; the scalar log-likelihoods are added on the host, predictions gathered by ctp), --fresh (every evaluation starts from zero root off-diagonals, i.e. is a pure
 //     function of the parameters; enables speculative batching of the simplex moves), --sparse_joints (one line per
 //     joint instead of the dense matrix whose size is quadratic in the data set).
 #include <cstdio>
@@ -22,6 +23,8 @@
 #include <fstream>
 #include <iomanip>
 #include <iostream>
+#include <memory>
+#include <thread>
 
 #include "ggp_data.hpp"
 #include "ggp_neldermead.hpp"
@@ -38,7 +41,7 @@ struct Session {
     int iteration = 0;        // likelihood.h:7
     bool save_ll = false;     // likelihood.h:9
     std::ofstream file_iteration;
-    int device = 0;
+    std::vector<int> devices{0};   // --devices: trees are sharded over these (one forest handle per device)
     bool fresh = false;
 };
 
@@ -46,38 +49,73 @@ void check(int rc, const char* what) {
     if (rc != GGP_OK) throw std::runtime_error(std::string(what) + ": " + ggp_last_error());
 }
 
-// one data slice on the device + the roots' persistent covariance (the reference's MOMAdata::cov of the roots)
-class DeviceForest {
+// what the running modes need from "the data on the GPU(s)"
+class Forest {
 public:
-    DeviceForest(const LineageTable& T, int device) : table_(T) {
-        const ggp_forest_desc d = make_desc(T, device);
+    virtual ~Forest() = default;
+    virtual const LineageTable& table() const = 0;
+    // +log-likelihood of each vector, evaluated as if one after the other (likelihood.h:170-174)
+    virtual std::vector<double> loglik(Session& S, const std::vector<std::vector<double>>& P) = 0;
+    // combined predictions [n_ctp][20] in the table's ctp order (main.cpp:132-140)
+    virtual void predict(const std::vector<double>& P, int n_seg, std::vector<double>& comb) = 0;
+    virtual ggp_forest* joints_handle() = 0;   // a handle that holds the whole table and its predictions, or nullptr
+};
+
+struct LoglikResult {
+    int rc = GGP_OK;
+    std::vector<double> ll;
+    std::vector<ggp_nan_info> nan;
+    std::string error;
+};
+
+[[noreturn]] void report_nan(Session& S, const LineageTable& T, int64_t cell, int64_t t_index, const std::vector<double>& p) {
+    S.log << "(sc_likelihood) ERROR: Log likelihood is Nan\n_____________________________\nCell: " << T.cell_id[cell]
+          << ", observation: " << t_index << "\nParameters:";
+    for (double x : p) S.log << " " << std::setprecision(15) << x;
+    S.log << "\n";
+    throw std::domain_error("Likelihood is Nan");
+}
+
+// one data slice on one device + the roots' persistent covariance (the reference's MOMAdata::cov of the roots)
+class DeviceForest : public Forest {
+public:
+    // init_f / init_r: the init_cells statistics to use (nullptr: those of this table, as init_cells(cells) computes them)
+    DeviceForest(const LineageTable& T, int device, const double* init_f = nullptr, const double* init_r = nullptr) : table_(T) {
+        ggp_forest_desc d = make_desc(T, device);
+        if (init_f && init_r) {
+            d.compute_init = 0;
+            for (int i = 0; i < 4; ++i) { d.init_f[i] = init_f[i]; d.init_r[i] = init_r[i]; }
+        }
         check(ggp_forest_create(&d, &h_), "ggp_forest_create");
         carry_.assign((size_t)ggp_forest_n_roots(h_) * 16, 0.0);
     }
-    ~DeviceForest() { ggp_forest_destroy(h_); }
+    ~DeviceForest() override { ggp_forest_destroy(h_); }
     DeviceForest(const DeviceForest&) = delete;
     ggp_forest* handle() const { return h_; }
-    const LineageTable& table() const { return table_; }
+    const LineageTable& table() const override { return table_; }
+    ggp_forest* joints_handle() override { return h_; }
 
-    // +log-likelihood of each vector, evaluated as if one after the other (likelihood.h:170-174)
-    std::vector<double> loglik(Session& S, const std::vector<std::vector<double>>& P) {
+    LoglikResult loglik_raw(const std::vector<double>& flat, int n_vec, bool fresh) {
+        LoglikResult R;
+        R.ll.resize(n_vec);
+        R.nan.resize(n_vec);
+        R.rc = ggp_loglik(h_, flat.data(), n_vec, fresh ? nullptr : carry_.data(), R.ll.data(), nullptr, R.nan.data());
+        if (R.rc != GGP_OK && R.rc != GGP_ERR_NAN) R.error = ggp_last_error();
+        return R;
+    }
+    std::vector<double> loglik(Session& S, const std::vector<std::vector<double>>& P) override {
         std::vector<double> flat;
         for (const auto& p : P) flat.insert(flat.end(), p.begin(), p.end());
-        std::vector<double> out(P.size());
-        std::vector<ggp_nan_info> nan(P.size());
-        const int rc = ggp_loglik(h_, flat.data(), (int32_t)P.size(), S.fresh ? nullptr : carry_.data(), out.data(), nullptr, nan.data());
-        if (rc == GGP_ERR_NAN) {
+        LoglikResult R = loglik_raw(flat, (int)P.size(), S.fresh);
+        if (R.rc == GGP_ERR_NAN)
             for (size_t v = 0; v < P.size(); ++v)
-                if (nan[v].cell >= 0) {
-                    S.log << "(sc_likelihood) ERROR: Log likelihood is Nan\n_____________________________\nCell: "
-                          << table_.cell_id[nan[v].cell] << ", observation: " << nan[v].t_index << "\nParameters:";
-                    for (double x : P[v]) S.log << " " << std::setprecision(15) << x;
-                    S.log << "\n";
-                    throw std::domain_error("Likelihood is Nan");
-                }
-        }
-        check(rc, "ggp_loglik");
-        return out;
+                if (R.nan[v].cell >= 0) report_nan(S, table_, R.nan[v].cell, R.nan[v].t_index, P[v]);
+        if (R.rc != GGP_OK) throw std::runtime_error("ggp_loglik: " + R.error);
+        return R.ll;
+    }
+    void predict(const std::vector<double>& P, int n_seg, std::vector<double>& comb) override {
+        comb.resize((size_t)table_.n_ctp() * 20);
+        check(ggp_predict(h_, P.data(), n_seg, nullptr, nullptr, comb.data()), "ggp_predict");
     }
 
 private:
@@ -85,6 +123,129 @@ private:
     ggp_forest* h_ = nullptr;
     std::vector<double> carry_;
 };
+
+// The table's trees sharded over several devices: roots are bin-packed by cell-timepoint count, every
+// descendant stays with its root, the init_cells statistics are those of the whole table.  One handle and one host
+// thread per device; the per-shard log-likelihoods are added in shard order, predictions are scattered back by ctp.
+class ShardedForest : public Forest {
+public:
+    ShardedForest(const LineageTable& T, const std::vector<int>& devices) : table_(T) {
+        const int64_t N = T.n_cells();
+        const int D = (int)devices.size();
+        // tree of every cell (parents may come after daughters in the file)
+        std::vector<int32_t> root_of(N, -1);
+        for (int64_t c = 0; c < N; ++c) {
+            int64_t u = c;
+            std::vector<int64_t> chain;
+            while (root_of[u] < 0 && T.parent[u] >= 0) { chain.push_back(u); u = T.parent[u]; }
+            const int32_t r = root_of[u] >= 0 ? root_of[u] : (int32_t)u;
+            root_of[u] = r;
+            for (int64_t w : chain) root_of[w] = r;
+        }
+        std::vector<int64_t> size(N, 0);
+        std::vector<int32_t> roots;
+        for (int64_t c = 0; c < N; ++c) {
+            size[root_of[c]] += T.n_points(c);
+            if (T.parent[c] < 0) roots.push_back((int32_t)c);
+        }
+        std::stable_sort(roots.begin(), roots.end(), [&](int32_t a, int32_t b) { return size[a] > size[b]; });
+        std::vector<int64_t> load(D, 0);
+        std::vector<int32_t> shard_of_root(N, 0);
+        for (int32_t r : roots) {
+            const int k = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+            shard_of_root[r] = k;
+            load[k] += size[r];
+        }
+        // sub-tables in file order
+        tables_.resize(D);
+        cells_.resize(D);
+        ctp_.resize(D);
+        std::vector<int32_t> local(N, -1);
+        for (int64_t c = 0; c < N; ++c) {
+            const int k = shard_of_root[root_of[c]];
+            local[c] = (int32_t)cells_[k].size();
+            cells_[k].push_back(c);
+        }
+        for (int k = 0; k < D; ++k) {
+            LineageTable& Sx = tables_[k];
+            Sx.noise_model = T.noise_model; Sx.division_model = T.division_model; Sx.fp_auto = T.fp_auto;
+            auto rm = [&](int32_t c) { return c < 0 ? -1 : local[c]; };
+            for (int64_t c : cells_[k]) {
+                Sx.cell_id.push_back(T.cell_id[c]); Sx.parent_id.push_back(T.parent_id[c]);
+                Sx.parent.push_back(rm(T.parent[c])); Sx.daughter1.push_back(rm(T.daughter1[c])); Sx.daughter2.push_back(rm(T.daughter2[c]));
+                for (int64_t i = T.offset[c]; i < T.offset[c + 1]; ++i) {
+                    Sx.time.push_back(T.time[i]); Sx.log_length.push_back(T.log_length[i]); Sx.fp.push_back(T.fp[i]);
+                    Sx.segment.push_back(T.segment[i]);
+                    ctp_[k].push_back(i);
+                }
+                Sx.offset.push_back((int64_t)Sx.time.size());
+            }
+        }
+        double init_f[4], init_r[4];
+        const ggp_forest_desc whole = make_desc(T, devices[0]);
+        check(ggp_init_stats(&whole, init_f, init_r), "ggp_init_stats");
+        for (int k = 0; k < D; ++k)
+            if (tables_[k].n_cells() > 0) forests_.emplace_back(new DeviceForest(tables_[k], devices[k], init_f, init_r));
+            else forests_.emplace_back(nullptr);
+    }
+    const LineageTable& table() const override { return table_; }
+    ggp_forest* joints_handle() override { return nullptr; }
+
+    std::vector<double> loglik(Session& S, const std::vector<std::vector<double>>& P) override {
+        std::vector<double> flat;
+        for (const auto& p : P) flat.insert(flat.end(), p.begin(), p.end());
+        const int D = (int)forests_.size(), n_vec = (int)P.size();
+        std::vector<LoglikResult> R(D);
+        std::vector<std::thread> th;
+        for (int k = 0; k < D; ++k)
+            if (forests_[k]) th.emplace_back([&, k] { R[k] = forests_[k]->loglik_raw(flat, n_vec, S.fresh); });
+        for (auto& t : th) t.join();
+        std::vector<double> ll(n_vec, 0.0);
+        for (int k = 0; k < D; ++k) {
+            if (!forests_[k]) continue;
+            if (R[k].rc != GGP_OK && R[k].rc != GGP_ERR_NAN) throw std::runtime_error("ggp_loglik (shard " + std::to_string(k) + "): " + R[k].error);
+            for (int v = 0; v < n_vec; ++v) ll[v] = ll[v] + R[k].ll[v];
+        }
+        // first NaN: the first vector that has one; among the shards the tree that comes first in the file
+        for (int v = 0; v < n_vec; ++v) {
+            int64_t best = -1, best_t = -1;
+            for (int k = 0; k < D; ++k)
+                if (forests_[k] && R[k].nan[v].cell >= 0) {
+                    const int64_t g = cells_[k][R[k].nan[v].cell];
+                    if (best < 0 || g < best) { best = g; best_t = R[k].nan[v].t_index; }
+                }
+            if (best >= 0) report_nan(S, table_, best, best_t, P[v]);
+        }
+        return ll;
+    }
+    void predict(const std::vector<double>& P, int n_seg, std::vector<double>& comb) override {
+        comb.assign((size_t)table_.n_ctp() * 20, 0.0);
+        const int D = (int)forests_.size();
+        std::vector<std::vector<double>> part(D);
+        std::vector<std::string> err(D);
+        std::vector<std::thread> th;
+        for (int k = 0; k < D; ++k)
+            if (forests_[k]) th.emplace_back([&, k] {
+                try { forests_[k]->predict(P, n_seg, part[k]); } catch (std::exception& e) { err[k] = e.what(); }
+            });
+        for (auto& t : th) t.join();
+        for (int k = 0; k < D; ++k) {
+            if (!err[k].empty()) throw std::runtime_error(err[k]);
+            for (size_t i = 0; i < ctp_[k].size(); ++i) std::memcpy(&comb[20 * (size_t)ctp_[k][i]], &part[k][20 * i], 20 * sizeof(double));
+        }
+    }
+
+private:
+    const LineageTable& table_;
+    std::vector<LineageTable> tables_;
+    std::vector<std::vector<int64_t>> cells_, ctp_;
+    std::vector<std::unique_ptr<DeviceForest>> forests_;
+};
+
+std::unique_ptr<Forest> make_forest(Session& S, const LineageTable& T) {
+    if (S.devices.size() > 1) return std::unique_ptr<Forest>(new ShardedForest(T, S.devices));
+    return std::unique_ptr<Forest>(new DeviceForest(T, S.devices[0]));
+}
 
 // bookkeeping of one evaluation (likelihood.h:138-158): counter, iterations file, stdout
 void record_evaluation(Session& S, const std::vector<double>& p, double tl) {
@@ -101,7 +262,7 @@ void record_evaluation(Session& S, const std::vector<double>& p, double tl) {
     }
 }
 
-std::vector<double> total_likelihood(Session& S, DeviceForest& F, const std::vector<std::vector<double>>& P, bool record = true) {
+std::vector<double> total_likelihood(Session& S, Forest& F, const std::vector<std::vector<double>>& P, bool record = true) {
     std::vector<double> ll = F.loglik(S, P);
     if (record) for (size_t v = 0; v < P.size(); ++v) record_evaluation(S, P[v], ll[v]);
     return ll;
@@ -149,7 +310,7 @@ std::vector<double> invert(std::vector<double> A, int n) {
 }
 
 // squared error bars from the numerical Hessian (likelihood.h:211-269), the whole stencil in one launch
-std::vector<double> ll_error_bars(Session& S, DeviceForest& F, const ParameterSet& params, double epsilon) {
+std::vector<double> ll_error_bars(Session& S, Forest& F, const ParameterSet& params, double epsilon) {
     const std::vector<double> x = params.get_final();
     const std::vector<int> idx = params.non_fixed();
     const int n = (int)idx.size();
@@ -176,7 +337,7 @@ std::vector<double> ll_error_bars(Session& S, DeviceForest& F, const ParameterSe
     return err;
 }
 
-void save_error_bars(Session& S, DeviceForest& F, const std::string& outfile, const ParameterSet& params) {
+void save_error_bars(Session& S, Forest& F, const std::string& outfile, const ParameterSet& params) {
     std::ofstream f(outfile, std::ios_base::app);
     f << "\nerrors^2:\nepsilon";
     const std::vector<int> idx = params.non_fixed();
@@ -213,7 +374,8 @@ void run_minimization(Session& S, const LineageTable& T, ParameterSet& params, i
     setup_outfile_likelihood(outfile_ll, params);
     S.log << "Outfile: " << outfile_ll << "\n";
 
-    DeviceForest F(T, S.device);
+    const std::unique_ptr<Forest> Fp = make_forest(S, T);
+    Forest& F = *Fp;
     const bool log_space = S.args["search_space"] == "log";
     const double tolerance = std::stod(S.args["tolerance_maximization"]);
     const size_t n = params.all.size();
@@ -271,7 +433,8 @@ void run_minimization(Session& S, const LineageTable& T, ParameterSet& params, i
 
 void run_bound_1dscan(Session& S, const LineageTable& T, const ParameterSet& params, int segment) {
     S.log << "-> 1d Scan\n";
-    DeviceForest F(T, S.device);
+    const std::unique_ptr<Forest> Fp = make_forest(S, T);
+    Forest& F = *Fp;
     S.save_ll = true;
     for (size_t i = 0; i < params.all.size(); ++i) {
         const Parameter& p = params.all[i];
@@ -305,13 +468,13 @@ std::string prediction_base(Session& S, const std::vector<ParameterSet>& list) {
     return f;
 }
 
-void run_prediction_segments(Session& S, DeviceForest& F, std::vector<ParameterSet>& list) {
+void run_prediction_segments(Session& S, Forest& F, std::vector<ParameterSet>& list) {
     S.log << "-> prediction\n";
     const LineageTable& T = F.table();
     const std::string outfile = prediction_base(S, list) + "_prediction.csv";
     const std::vector<double> P = flatten_params(list);
-    std::vector<double> comb((size_t)T.n_ctp() * 20);
-    check(ggp_predict(F.handle(), P.data(), (int32_t)list.size(), nullptr, nullptr, comb.data()), "ggp_predict");
+    std::vector<double> comb;
+    F.predict(P, (int)list.size(), comb);
     S.log << "Outfile: " << outfile << "\n";
     for (size_t i = 0; i < list.size(); ++i) list[i].to_csv(outfile, i == 0 ? std::ios_base::out : std::ios_base::app);
     std::ofstream f(outfile, std::ios_base::app);
@@ -327,9 +490,20 @@ void run_prediction_segments(Session& S, DeviceForest& F, std::vector<ParameterS
         }
 }
 
-void run_joint_distribution(Session& S, DeviceForest& F, std::vector<ParameterSet>& list) {
+void run_joint_distribution(Session& S, Forest& Fx, std::vector<ParameterSet>& list) {
     S.log << "-> joint posteriors\n";
-    const LineageTable& T = F.table();
+    const LineageTable& T = Fx.table();
+    // the joints follow both daughters of every cell and are written in the file's row order: they run on one handle
+    // that holds the whole table (with several devices: a second pass of -p on the first device)
+    std::unique_ptr<DeviceForest> whole;
+    ggp_forest* handle = Fx.joints_handle();
+    if (!handle) {
+        S.log << "(joints run on device " << S.devices[0] << " only)\n";
+        whole.reset(new DeviceForest(T, S.devices[0]));
+        std::vector<double> tmp;
+        whole->predict(flatten_params(list), (int)list.size(), tmp);
+        handle = whole->handle();
+    }
     const std::vector<double> P = flatten_params(list);
     const double tol = std::stod(S.args["rel_tolerance_joints"]);
     const bool sparse = S.args.count("sparse_joints") > 0;
@@ -353,9 +527,9 @@ void run_joint_distribution(Session& S, DeviceForest& F, std::vector<ParameterSe
     for (int64_t r0 = 0; r0 < M; r0 += block) {
         const int64_t r1 = std::min(M, r0 + block);
         int64_t n = 0;
-        check(ggp_joints(F.handle(), P.data(), (int32_t)list.size(), tol, r0, r1, 0, &n, nullptr, nullptr, nullptr), "ggp_joints");
+        check(ggp_joints(handle, P.data(), (int32_t)list.size(), tol, r0, r1, 0, &n, nullptr, nullptr, nullptr), "ggp_joints");
         row.resize(std::max<int64_t>(n, 1)); col.resize(std::max<int64_t>(n, 1)); rec.resize((size_t)std::max<int64_t>(n, 1) * 44);
-        check(ggp_joints(F.handle(), P.data(), (int32_t)list.size(), tol, r0, r1, n, &n, row.data(), col.data(), rec.data()), "ggp_joints");
+        check(ggp_joints(handle, P.data(), (int32_t)list.size(), tol, r0, r1, n, &n, row.data(), col.data(), rec.data()), "ggp_joints");
         int64_t at = 0;
         for (int64_t r = r0; r < r1; ++r) {
             const int64_t c = cell_of[r];
@@ -398,6 +572,7 @@ Args arg_parser(int argc, char** argv) {
         {"-p", "--predict", "run prediction"},
         {"-j", "--joints", "run calculation of joint probabilities"},
         {"-d", "--device", "(ggp-b200) CUDA device ordinal, default: 0"},
+        {"-ds", "--devices", "(ggp-b200) comma separated CUDA device ordinals: lineage trees are sharded over them"},
         {"-fresh", "--fresh", "(ggp-b200) history-free evaluations, speculative batching of simplex moves"},
         {"-sj", "--sparse_joints", "(ggp-b200) write one line per joint instead of the dense matrix"}};
     Args a;
@@ -430,6 +605,7 @@ Args arg_parser(int argc, char** argv) {
             else if (key == "-p") a["predict"] = "1";
             else if (key == "-j") { a["joints"] = "1"; a["predict"] = "1"; }
             else if (key == "-d") a["device"] = value(i);
+            else if (key == "-ds") a["devices"] = value(i);
             else if (key == "-fresh") a["fresh"] = "1";
             else if (key == "-sj") a["sparse_joints"] = "1";
             else if (key == "-h") {
@@ -465,7 +641,8 @@ int main(int argc, char** argv) {
         S.args = arg_parser(argc, argv);
         if (S.args.count("help")) return EXIT_SUCCESS;
         S.print_level = std::stoi(S.args["print_level"]);
-        S.device = std::stoi(S.args["device"]);
+        S.devices.clear();
+        for (const auto& d : split(S.args.count("devices") ? S.args["devices"] : S.args["device"], ",")) S.devices.push_back(std::stoi(trim(d)));
         S.fresh = S.args.count("fresh") > 0;
         const std::string log_base = out_dir(S.args) + file_base(S.args["infile"]);
         outfile_log = log_base + ".log";
@@ -509,9 +686,9 @@ int main(int argc, char** argv) {
             }
         if (S.args.count("predict")) {
             build_genealogy(cells, S.log);
-            DeviceForest F(cells, S.device);
-            run_prediction_segments(S, F, params_list);
-            if (S.args.count("joints")) run_joint_distribution(S, F, params_list);   // needs the predictions on the device
+            const std::unique_ptr<Forest> F = make_forest(S, cells);
+            run_prediction_segments(S, *F, params_list);
+            if (S.args.count("joints")) run_joint_distribution(S, *F, params_list);   // needs the predictions on the device
         }
         S.log << "Done." << std::endl;
         std::cout << "Done. Log file: " << outfile_log_success << std::endl;

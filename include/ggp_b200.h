@@ -84,6 +84,10 @@ int64_t ggp_forest_n_generations(const ggp_forest* f);
  * new measurements (and by bench.py's end-to-end leg). */
 int ggp_forest_upload_series(ggp_forest* f, const double* time, const double* log_length, const double* fp);
 int ggp_forest_get_init(const ggp_forest* f, double* init_f4, double* init_r4);
+/* the init_cells_f / init_cells_r statistics of a data set (moma_input.h:675-735) without creating a forest: what a caller
+ * that shards trees over several handles passes to every shard (compute_init = 0).  Host arithmetic on the descriptor's
+ * arrays (input preparation, not part of the device path). */
+int ggp_init_stats(const ggp_forest_desc* desc, double* init_f4, double* init_r4);
 
 /* replaces: total_likelihood(params_vec, cells) (likelihood.h:170-174; objective :125-159) for n_vec
  * parameter vectors at once (scan main.cpp:105-108, Hessian stencil likelihood.h:211-258, simplex).

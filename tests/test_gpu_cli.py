@@ -183,3 +183,22 @@ def test_nan_is_reported_like_the_reference(tmp_path):
     assert "Likelihood is Nan" in r.stdout
     log = open(os.path.join(out, "forest_error.log")).read()
     assert "Log likelihood is Nan" in log and "Cell: 1.1, observation: 0" in log
+
+
+def test_devices_option_shards_trees(tmp_path):
+    """--devices a,b: trees sharded over several handles (here twice the same GPU), log-likelihoods added on the host,
+    predictions gathered by ctp: same files as the single-device run (totals to rounding, predictions identical)"""
+    P = ggp.PARAMS_SCALED_BINOMIAL
+    data = ggp.simulate_forest(9, 3, noise_model="scaled", division_model="binomial", seed=23, pts_range=(3, 8))
+    csv, cfg = write_inputs(tmp_path, data)
+    pf = write_params(tmp_path / "p.txt", P, bound=(3,))
+    outs = []
+    for extra, name in (([], "one"), (["--devices", "0,0,0"], "three")):
+        out = str(tmp_path / name)
+        run(["-i", csv, "-b", pf, "-c", cfg, "-s", "-p", "-j", "-o", out] + extra)
+        sc = read_table(os.path.join(out, "forest_scan_mean_q.csv"), "iteration,")
+        pr = read_table(os.path.join(out, "forest_f_b3_prediction.csv"), "cell_id,parent_id,time")
+        jn = open(os.path.join(out, "forest_f_b3_joints.csv")).read()
+        outs.append((np.array([[float(x) for x in r[1:]] for r in sc]), pr, jn))
+    assert outs[0][1] == outs[1][1] and outs[0][2] == outs[1][2]
+    assert max_rel(outs[1][0][:, 11], outs[0][0][:, 11]) < 1e-13 and np.array_equal(outs[1][0][:, :11], outs[0][0][:, :11])

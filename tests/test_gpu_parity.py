@@ -285,3 +285,44 @@ def test_streamed_upload_evaluates_chunk_by_chunk(chunks, monkeypatch):
         ref = Oracle(d).predictions([P] * (int(d.segment.max()) + 1))
         assert same_bits(pr["prediction"][0], ref["prediction"][0])
         f.close()
+
+
+@pytest.mark.gpu
+def test_sharded_predictions_and_joints_gather_to_the_unsharded_result():
+    """trees shard across ranks (bin packing by cell-timepoints, descendants stay with their root, the
+    init_cells statistics are those of the whole data set); -p / -j outputs stay sharded by ctp and gather by index.
+    Three shards evaluated on this GPU reproduce the single-forest result bit for bit."""
+    from gfp_gaussian_process_b200 import sharding
+    P = ggp.PARAMS_SCALED_BINOMIAL
+    d = ggp.simulate_forest(11, 4, noise_model="scaled", division_model="binomial", seed=41, pts_range=(3, 9))
+    full = ggp.Forest(d)
+    ll_full, pc_full = ggp.total_likelihood(P, full, per_cell=True)
+    pr_full = ggp.prediction_forward_backward(full, [P])
+    r_full, c_full, m_full, v_full = ggp.collect_joint_distributions(full, [P], 1e-10)
+    world = 3
+    parts = sharding.partition_roots(d, world)
+    assert sorted(np.concatenate(parts).tolist()) == d.roots().tolist()
+    pc = np.full(d.n_cells, np.nan)
+    pred = {k: (np.full((d.n_ctp, 4), np.nan), np.full((d.n_ctp, 4, 4), np.nan)) for k in ("forward", "backward", "prediction")}
+    joints = []
+    for rank in range(world):
+        sub, cells, ctp = sharding.shard(d, rank, world)
+        f = ggp.Forest(sub)
+        _, pcs = ggp.total_likelihood(P, f, per_cell=True)
+        pc[cells] = pcs
+        pr = ggp.prediction_forward_backward(f, [P])
+        for k in pred:
+            pred[k][0][ctp] = pr[k][0]
+            pred[k][1][ctp] = pr[k][1]
+        r, c, m, v = ggp.collect_joint_distributions(f, [P], 1e-10)
+        joints.append((ctp[r], ctp[c], m, v))
+        f.close()
+    assert same_bits(pc, pc_full)
+    for k in pred:
+        assert same_bits(pred[k][0], pr_full[k][0]) and same_bits(pred[k][1], pr_full[k][1])
+    r = np.concatenate([j[0] for j in joints]); c = np.concatenate([j[1] for j in joints])
+    m = np.concatenate([j[2] for j in joints]); v = np.concatenate([j[3] for j in joints])
+    order = np.lexsort((c, r))
+    assert np.array_equal(r[order], r_full) and np.array_equal(c[order], c_full)
+    assert same_bits(m[order], m_full) and same_bits(v[order], v_full)
+    full.close()

@@ -326,3 +326,30 @@ def test_sharded_predictions_and_joints_gather_to_the_unsharded_result():
     assert np.array_equal(r[order], r_full) and np.array_equal(c[order], c_full)
     assert same_bits(m[order], m_full) and same_bits(v[order], v_full)
     full.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", [101, 102, 103, 104])
+def test_random_forests_all_passes_bitwise(seed):
+    """random shapes (tree counts that do not fill a 32-cell group, very short and long cells, 1-3 segments, both models):
+    per-cell sums, forward / backward / combined predictions and the backward cell state against the oracle, bit for bit"""
+    rng = np.random.default_rng(seed)
+    noise, division = [("const", "gauss"), ("scaled", "binomial"), ("scaled", "gauss"), ("const", "binomial")][seed % 4]
+    P0 = ggp.PARAMS_CONST_GAUSS if noise == "const" else ggp.PARAMS_SCALED_BINOMIAL
+    n_seg = int(rng.integers(1, 4))
+    d = ggp.simulate_forest(int(rng.integers(1, 70)), int(rng.integers(1, 6)), params=P0, noise_model=noise, division_model=division,
+                            seed=seed, pts_range=(1, int(rng.integers(2, 40))), n_segments=n_seg, fp_auto=float(rng.integers(0, 3)))
+    P = np.stack([P0 * (1 + 0.05 * rng.standard_normal(11)) for _ in range(n_seg)])
+    f = ggp.Forest(d)
+    o = Oracle(d)
+    if n_seg == 1:
+        vecs = np.stack([P[0], P[0] * 1.02, P[0] * 0.97])
+        ll, pc = ggp.total_likelihood(vecs, f, per_cell=True, raise_on_nan=False)
+        for i in range(3):
+            assert same_bits(pc[i], o.total_loglik(vecs[i], per_cell=True)[1])
+    pr, ref = ggp.prediction_forward_backward(f, P), o.predictions(P)
+    for k in ("forward", "backward", "prediction"):
+        assert same_bits(pr[k][0], ref[k][0]) and same_bits(pr[k][1], ref[k][1]), k
+    bm, bc = ggp.api.backward_cell_state(f)
+    assert same_bits(bm, o.cell_mean) and same_bits(bc.reshape(-1, 16), o.cell_cov)
+    f.close()

@@ -109,6 +109,12 @@ __global__ void __launch_bounds__(GGP_COOP_BLOCK(NG), NG == 1 ? 3 : 4 / NG) ggp_
         for (int i = 0; i < NG * GGP_COOP_ROLES; ++i) max_steps = max(max_steps, s_steps[i]);
     }
     const GgpOuParams ou_lik = ggp_ou(sp, false);   // LIK: one parameter vector for the whole block
+    // pow(gamma_lambda, 3) depends on the parameters only: once per thread (LIK) / per staged segment (PRED), not per step
+    __shared__ double s_gl3[GGP_COOP_SEG_SMEM];
+    if (PRED && seg_staged && (int)threadIdx.x < A.n_seg) s_gl3[threadIdx.x] = ggp_pow(sp[GGP_NP * threadIdx.x + 1], 3.0, &T);
+    if (PRED) __syncthreads();
+    const double gl3_lik = (!PRED && role == 3) ? ggp_pow(sp[1], 3.0, &T) : GGP_NO_GL3;
+    int prev_seg = -1;   // PRED: segment of the previous step's parameters (the elementary exponentials are reused if unchanged)
     // The measurements of a step (t_to, t_from, x, g) sit in scratch slots GGP_CS_IN + 4 * (step & 1); role 0 fetches
     // those of the NEXT step with cp.async while the current step computes (the loads retire behind a whole step
     // of arithmetic and occupy no registers).
@@ -143,12 +149,16 @@ __global__ void __launch_bounds__(GGP_COOP_BLOCK(NG), NG == 1 ? 3 : 4 / NG) ggp_
         }
         if (live) {
             const double dt = S[in + 0] - S[in + 1];
-            ggp_coop_run_phase(0, role, S, PRED ? ggp_ou(p, false) : ou_lik, dt, &T);
+            // same dt (and parameters) as this cell's previous step: GGP_CS_GE still holds the elementary exponentials
+            const bool ge_same = role == 0 && it > 0 && dt == S[GGP_CS_K + GGP_K_T] && (!PRED || seg_from == prev_seg);
+            ggp_coop_run_phase(0, role, S, PRED ? ggp_ou(p, false) : ou_lik, dt, &T, ge_same);
+            prev_seg = seg_from;
         }
         ggp_coop_sync<GS>(group);
 #pragma unroll
         for (int ph = 1; ph < GGP_COOP_PHASES; ++ph) {
-            if (live) ggp_coop_run_phase(ph, role, S, PRED ? ggp_ou(p, false) : ou_lik, 0.0, &T);
+            if (live) ggp_coop_run_phase(ph, role, S, PRED ? ggp_ou(p, false) : ou_lik, 0.0, &T, false,
+                                         PRED ? (seg_staged ? s_gl3[seg_from] : GGP_NO_GL3) : gl3_lik);
             ggp_coop_sync<GS>(group);
         }
         if (live) {

@@ -26,6 +26,7 @@
 #include <memory>
 #include <thread>
 
+#include "ggp_correlation.hpp"
 #include "ggp_data.hpp"
 #include "ggp_neldermead.hpp"
 #include "ggp_params.hpp"
@@ -553,6 +554,53 @@ void run_joint_distribution(Session& S, Forest& Fx, std::vector<ParameterSet>& l
     }
 }
 
+// correlation functions (python_src/correlation_from_joint.py) from the joints on the device, no joints file in between
+CorrelationSet make_correlation_set(Session& S) {
+    const double dt = std::stod(S.args["correlation"]), n_data = std::stod(S.args["n_data"]);
+    if (S.args.count("normalize_time")) return CorrelationSet(0.05, 3.0, 0.024);   // process_file :688-693
+    return CorrelationSet(dt, dt * n_data, dt * 0.2);                              // :681-685
+}
+
+void run_correlation(Session& S, Forest& Fx, std::vector<ParameterSet>& list) {
+    S.log << "-> correlation functions\n";
+    const LineageTable& T = Fx.table();
+    const std::vector<double> P = flatten_params(list);
+    const double tol = std::stod(S.args["rel_tolerance_joints"]);
+    std::unique_ptr<DeviceForest> whole;
+    ggp_forest* handle = Fx.joints_handle();
+    std::vector<double> comb;
+    if (!handle) {
+        whole.reset(new DeviceForest(T, S.devices[0]));
+        handle = whole->handle();
+    }
+    check(ggp_predict(handle, P.data(), (int32_t)list.size(), nullptr, nullptr, nullptr), "ggp_predict");
+    comb.resize((size_t)T.n_ctp() * 20);
+    check(ggp_predict(handle, P.data(), (int32_t)list.size(), nullptr, nullptr, comb.data()), "ggp_predict");
+    std::vector<double> m14((size_t)T.n_ctp() * 14);
+    for (int64_t k = 0; k < T.n_ctp(); ++k) {
+        const double* r = comb.data() + 20 * k;
+        double* o = m14.data() + 14 * k;
+        for (int i = 0; i < 4; ++i) o[i] = r[i];
+        int q = 4;
+        for (int a = 0; a < 4; ++a) for (int b = a; b < 4; ++b) o[q++] = r[4 + 4 * a + b];
+    }
+    JointsSource src;
+    src.marginal14 = [&](int64_t k) { return m14.data() + 14 * k; };
+    src.joints_of_rows = [&](int64_t r0, int64_t r1, std::vector<int64_t>& row, std::vector<int64_t>& col, std::vector<double>& rec) {
+        int64_t n = 0;
+        check(ggp_joints(handle, P.data(), (int32_t)list.size(), tol, r0, r1, 0, &n, nullptr, nullptr, nullptr), "ggp_joints");
+        row.assign(std::max<int64_t>(n, 1), -1); col.assign(std::max<int64_t>(n, 1), -1); rec.assign((size_t)std::max<int64_t>(n, 1) * 44, 0.0);
+        check(ggp_joints(handle, P.data(), (int32_t)list.size(), tol, r0, r1, n, &n, row.data(), col.data(), rec.data()), "ggp_joints");
+        row.resize(n); col.resize(n);
+    };
+    CorrelationSet CS = make_correlation_set(S);
+    correlation_from_joints(CS, T.cell_id, T.parent_id, T.offset, T.time, src, S.args.count("normalize_time") > 0);
+    CS.finalize();
+    const std::string outfile = prediction_base(S, list) + "_correlations.csv";
+    S.log << "Outfile: " << outfile << "\n";
+    CS.to_csv(outfile);
+}
+
 // ---- command line (main.cpp:191-330) ------------------------------------------------------------------
 Args arg_parser(int argc, char** argv) {
     const std::vector<std::vector<std::string>> keys = {
@@ -574,10 +622,14 @@ Args arg_parser(int argc, char** argv) {
         {"-d", "--device", "(ggp-b200) CUDA device ordinal, default: 0"},
         {"-ds", "--devices", "(ggp-b200) comma separated CUDA device ordinals: lineage trees are sharded over them"},
         {"-fresh", "--fresh", "(ggp-b200) history-free evaluations, speculative batching of simplex moves"},
-        {"-sj", "--sparse_joints", "(ggp-b200) write one line per joint instead of the dense matrix"}};
+        {"-sj", "--sparse_joints", "(ggp-b200) write one line per joint instead of the dense matrix"},
+        {"-corr", "--correlation", "(ggp-b200) time between measurements: correlation functions straight from the joints (implies -p; no joints file)"},
+        {"-n_data", "--n_data", "(ggp-b200) number of lags of the correlation function, default: 200"},
+        {"-norm", "--normalize_time", "(ggp-b200) correlation over time in units of the cell cycle"},
+        {"-corr_files", "--correlation_files", "(ggp-b200) <prefix>_joints.csv: correlation functions from existing files (no GPU needed; use with -corr)"}};
     Args a;
     a["print_level"] = "0"; a["tolerance_maximization"] = "1e-10"; a["rel_tolerance_joints"] = "1e-10";
-    a["search_space"] = "log"; a["noise_model"] = "scaled"; a["cell_division_model"] = "binomial"; a["device"] = "0";
+    a["search_space"] = "log"; a["noise_model"] = "scaled"; a["cell_division_model"] = "binomial"; a["device"] = "0"; a["n_data"] = "200";
     auto value = [&](int i) -> std::string {
         if (i + 1 >= argc) throw std::invalid_argument(std::string("missing value after ") + argv[i]);
         return argv[i + 1];
@@ -608,6 +660,10 @@ Args arg_parser(int argc, char** argv) {
             else if (key == "-ds") a["devices"] = value(i);
             else if (key == "-fresh") a["fresh"] = "1";
             else if (key == "-sj") a["sparse_joints"] = "1";
+            else if (key == "-corr") { a["correlation"] = value(i); a["predict"] = "1"; }
+            else if (key == "-n_data") a["n_data"] = value(i);
+            else if (key == "-norm") a["normalize_time"] = "1";
+            else if (key == "-corr_files") a["correlation_files"] = value(i);
             else if (key == "-h") {
                 a["help"] = "1";
                 std::cout << "Usage: ./gfp_gaussian [-options]\n";
@@ -621,8 +677,10 @@ Args arg_parser(int argc, char** argv) {
     if (a["noise_model"] != "const" && a["noise_model"] != "scaled") bad("noise_model must be either 'const' or 'scaled', not " + a["noise_model"]);
     if (a["cell_division_model"] != "gauss" && a["cell_division_model"] != "binomial")
         bad("cell_division_model must be either 'gauss' or 'binomial', not " + a["cell_division_model"]);
+    if (a.count("correlation_files") && !a.count("infile")) a["infile"] = a["correlation_files"];
     if (!a.count("infile")) bad("Required infile flag not set!\n");
     if (!std::filesystem::exists(a["infile"])) bad("Infile " + a["infile"] + " not found (use '-h' for help)!\n");
+    if (a.count("correlation_files")) return a;
     if (!a.count("parameter_bounds") || a["parameter_bounds"].empty()) bad("Required parameter_bounds flag not set!\n");
     for (const auto& pf : split(a["parameter_bounds"], " "))
         if (!std::filesystem::exists(pf)) bad("Paramters bound file '" + pf + "' not found (use '-h' for help)!\n");
@@ -652,6 +710,21 @@ int main(int argc, char** argv) {
         std::cout << "Temporary log file '" << outfile_log << "' created\n";
         S.log << ggp_version() << "\n";
 
+        if (S.args.count("correlation_files")) {   // drop-in for correlation_from_joint.py on existing files
+            if (!S.args.count("correlation")) throw std::invalid_argument("--correlation_files needs --correlation <dt>");
+            const std::string jf = S.args["correlation_files"];
+            const size_t at = jf.rfind("joints");
+            if (at == std::string::npos) throw std::invalid_argument("--correlation_files: not a <prefix>_joints.csv file");
+            CorrelationSet CS = make_correlation_set(S);
+            correlation_from_files(CS, jf, std::string(jf).replace(at, 6, "prediction"), S.args.count("normalize_time") > 0);
+            CS.finalize();
+            const std::string out = std::string(jf).replace(at, std::string::npos, "correlations.csv");
+            CS.to_csv(out);
+            S.log << "Outfile: " << out << "\nDone." << std::endl;
+            std::cout << "Done. Log file: " << outfile_log_success << std::endl;
+            std::rename(outfile_log.c_str(), outfile_log_success.c_str());
+            return EXIT_SUCCESS;
+        }
         const std::vector<std::string> param_files = split(S.args["parameter_bounds"], " ");
         std::vector<ParameterSet> params_list;
         for (const auto& pf : param_files) {
@@ -689,6 +762,7 @@ int main(int argc, char** argv) {
             const std::unique_ptr<Forest> F = make_forest(S, cells);
             run_prediction_segments(S, *F, params_list);
             if (S.args.count("joints")) run_joint_distribution(S, *F, params_list);   // needs the predictions on the device
+            if (S.args.count("correlation")) run_correlation(S, *F, params_list);
         }
         S.log << "Done." << std::endl;
         std::cout << "Done. Log file: " << outfile_log_success << std::endl;

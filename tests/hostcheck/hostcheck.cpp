@@ -165,6 +165,115 @@ int hc_predict(const ggp_forest_desc* d, const double* params, int n_seg, double
     return 0;
 }
 
+// forward and backward prediction passes with the cooperative step, role by role, in the order of
+// ggp_loglik_coop_kernel<.., PRED = true> and ggp_backward_coop_kernel (ggp_coop_kernels.cuh)
+int hc_predict_coop(const ggp_forest_desc* d, const double* params, int n_seg, double* fwd, double* bwd, double* bstate_cells) {
+    GgpLayout L;
+    if (!L.build(d).empty() || L.max_seg >= n_seg) return -1;
+    double scratch[GGP_CS_COUNT];
+    const GgpScratch S{scratch, 1};
+    const GgpDevForest F = hc_dev(L, d);
+    std::vector<double> state((size_t)14 * L.n_cells), bstate((size_t)20 * L.n_cells);
+    for (int64_t slot = 0; slot < L.n_cells; ++slot) {   // forward: generation order
+        const int64_t off = F.s_off[slot];
+        const int n = F.s_n[slot], parent = F.s_parent[slot];
+        int t = 0;
+        int64_t from = off;
+        if (parent < 0) {
+            const double* p = params + GGP_NP * F.seg[off];
+            double mu[4], C[16];
+            for (int i = 0; i < 16; ++i) C[i] = 0.0;
+            mu[0] = F.init_f[0]; mu[1] = F.init_f[1];
+            C[0] = F.init_f[2];  C[5] = F.init_f[3];
+            mu[2] = p[0]; mu[3] = p[3];
+            C[10] = p[2] / (2. * p[1]);
+            C[15] = p[5] / (2. * p[4]);
+            const GgpMeas m = ggp_measure16(mu, C, F.x[off], F.g[off], p[7], p[8], F.model);
+            ggp_posterior16(mu, C, m);
+            ggp_store20(fwd + 20 * off, mu, C);
+            GgpState s;
+            ggp_state_from16(s, mu, C);
+            for (int k = 0; k < 4; ++k) S[GGP_CS_ST + k] = s.m[k];
+            for (int k = 0; k < 10; ++k) S[GGP_CS_ST + 4 + k] = s.c[k];
+        } else {
+            for (int k = 0; k < 14; ++k) S[GGP_CS_ST + k] = state[k * L.n_cells + parent];
+            t = -1;
+            from = F.s_off[parent] + F.s_n[parent] - 1;
+        }
+        while (t + 1 < n) {
+            const int64_t at = off + t + 1;
+            const double* p = params + GGP_NP * F.seg[from];
+            const double* pt = params + GGP_NP * F.seg[at];
+            const double dt = F.time[at] - F.time[from];
+            for (int ph = 0; ph < GGP_COOP_PHASES; ++ph)
+                for (int role = 0; role < GGP_COOP_ROLES; ++role) ggp_coop_run_phase(ph, role, S, ggp_ou(p, false), dt, &g_tables);
+            for (int role = 0; role < GGP_COOP_ROLES; ++role)
+                ggp_coop_ph3_pred<false>(role, S, t < 0, p, pt, F.x[at], F.g[at], F.model, &g_tables, fwd + 20 * at);
+            ++t;
+            from = at;
+        }
+        for (int k = 0; k < 14; ++k) state[k * L.n_cells + slot] = S[GGP_CS_ST + k];
+    }
+    for (int64_t slot = L.n_cells - 1; slot >= 0; --slot) {   // backward: leaves first
+        const int64_t off = F.s_off[slot];
+        const int n = F.s_n[slot], d1 = F.s_d1[slot], d2 = F.s_d2[slot];
+        const bool leaf = d1 < 0 && d2 < 0;
+        const int da = d1 >= 0 ? d1 : d2;
+        int t = leaf ? n - 1 : n;
+        int64_t from = leaf ? off + t : F.s_off[da];
+        const double* p0 = params + GGP_NP * F.seg[off + n - 1];
+        double mu[4], C[16], R[16], rm[4];
+        GgpState s;
+        if (leaf) {
+            const double* fs = fwd + 20 * from;
+            for (int i = 0; i < 16; ++i) C[i] = fs[4 + i];
+            mu[0] = F.init_r[0]; mu[1] = F.init_r[1];
+            C[0] = F.init_r[2];  C[5] = F.init_r[3];
+            mu[2] = -p0[0]; mu[3] = -p0[3];
+            C[10] = p0[2] / (2. * p0[1]);
+            C[15] = p0[5] / (2. * p0[4]);
+            ggp_reverse_mean(mu, rm);
+            ggp_reverse_cov(C, R);
+            ggp_store20(bwd + 20 * from, rm, R);
+            const GgpMeas m = ggp_measure16(mu, C, F.x[from], F.g[from], p0[7], p0[8], F.model);
+            ggp_posterior16(mu, C, m);
+            ggp_state_from16(s, mu, C);
+            if (t == 0) ggp_store20(bstate.data() + 20 * slot, mu, C);
+        } else {
+            const double* b1 = bstate.data() + 20 * (int64_t)da;
+            for (int i = 0; i < 4; ++i) mu[i] = b1[i];
+            for (int i = 0; i < 16; ++i) C[i] = b1[4 + i];
+            ggp_divide_r16(mu, C, p0[9], p0[10], F.model);
+            if (d1 >= 0 && d2 >= 0) {
+                const double* b2 = bstate.data() + 20 * (int64_t)d2;
+                double mu2[4];
+                for (int i = 0; i < 4; ++i) mu2[i] = b2[i];
+                for (int i = 0; i < 16; ++i) R[i] = b2[4 + i];
+                ggp_divide_r16(mu2, R, p0[9], p0[10], F.model);
+                ggp_multiply_gaussian(mu, C, mu2, R);
+            }
+            ggp_state_from16(s, mu, C);
+        }
+        for (int k = 0; k < 4; ++k) S[GGP_CS_ST + k] = s.m[k];
+        for (int k = 0; k < 10; ++k) S[GGP_CS_ST + 4 + k] = s.c[k];
+        while (t > 0) {
+            const int64_t at = off + t - 1;
+            const double* pp = params + GGP_NP * F.seg[at];
+            const double dt = F.time[from] - F.time[at];
+            for (int ph = 0; ph < GGP_COOP_PHASES; ++ph)
+                for (int role = 0; role < GGP_COOP_ROLES; ++role) ggp_coop_run_phase(ph, role, S, ggp_ou(pp, true), dt, &g_tables);
+            for (int role = 0; role < GGP_COOP_ROLES; ++role) ggp_coop_store_reversed(role, S, bwd + 20 * at);
+            --t;
+            for (int role = 0; role < GGP_COOP_ROLES; ++role)
+                ggp_coop_ph3_pred<false>(role, S, false, pp, pp, F.x[at], F.g[at], F.model, &g_tables, t == 0 ? bstate.data() + 20 * slot : nullptr);
+            from = at;
+        }
+    }
+    for (int64_t s = 0; s < L.n_cells; ++s)
+        for (int k = 0; k < 20; ++k) bstate_cells[20 * (int64_t)L.cell_of_slot[s] + k] = bstate[20 * s + k];
+    return 0;
+}
+
 // joints on the host: predict, per-ctp preparation, then one walk per start point (row), rows in ctp order;
 // returns the number of joints, writes at most cap (unsorted inside a row: emission order)
 long long hc_joints(const ggp_forest_desc* d, const double* params, int n_seg, double tol, long long cap, long long* row, long long* col, double* rec44) {

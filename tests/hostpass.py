@@ -81,6 +81,20 @@ def host_predict(data, params):
     return {"forward": sp(fwd), "backward": sp(bwd), "prediction": sp(comb), "bstate": sp(bstate)}
 
 
+def host_predict_coop(data, params):
+    """forward / backward passes with the cooperative step (what the GPU kernels run), on the host"""
+    p = np.ascontiguousarray(params, dtype=np.float64).reshape(-1, 11)
+    M = data.n_ctp
+    fwd, bwd = np.zeros((M, 20)), np.zeros((M, 20))
+    bstate = np.zeros((data.n_cells, 20))
+    d = make_desc(data)
+    rc = hc().hc_predict_coop(C.byref(d), p.ctypes.data_as(_lib.c_double_p), p.shape[0], fwd.ctypes.data_as(_lib.c_double_p),
+                              bwd.ctypes.data_as(_lib.c_double_p), bstate.ctypes.data_as(_lib.c_double_p))
+    assert rc == 0
+    sp = lambda a: (a[:, :4], a[:, 4:].reshape(-1, 4, 4))
+    return {"forward": sp(fwd), "backward": sp(bwd), "bstate": sp(bstate)}
+
+
 def host_joints(data, params, tol, cap):
     """sparse joints from the product's host-compiled code, sorted by (row, col)"""
     p = np.ascontiguousarray(params, dtype=np.float64).reshape(-1, 11)

@@ -12,6 +12,7 @@
 // role's instruction stream at about the same time: one instruction fetch serves NG groups) and group w / 4.
 //   NG = 1: 128 threads, 4 blocks per SM; finest granularity, used for generations with few cells
 //   NG = 2: 256 threads, 2 blocks per SM
+//   NG = 5: 640 threads, 1 block per SM, 96 registers per thread (a few spills) for 20 instead of 16 resident warps
 //   NG = 4: 512 threads, 1 block per SM; 4x fewer instruction-cache fills per cell (the step's hot code is ~75 kB,
 //           over twice the 32 kB L1.5 instruction cache, so every step streams from L2)
 #define GGP_COOP_BLOCK(NG) ((NG) * GGP_COOP_ROLES * 32)
@@ -34,7 +35,7 @@ __device__ __forceinline__ void ggp_cp_async_wait() { asm volatile("cp.async.wai
 // PRED = false: likelihood (likelihood.h:36-103, one parameter vector per blockIdx.y); PRED = true: prediction_forward
 // (predictions.h:93-150): parameters by segment, the posterior of every point stored to A.out_fwd.
 template <int NG, bool GS, bool STEP_ALIGN = false, bool PRED = false>
-__global__ void __launch_bounds__(GGP_COOP_BLOCK(NG), NG == 1 ? 3 : 4 / NG) ggp_loglik_coop_kernel(const GgpDevForest F, const GgpFwdArgs A) {
+__global__ void __launch_bounds__(GGP_COOP_BLOCK(NG), NG == 1 ? 3 : (NG <= 4 ? 4 / NG : 1)) ggp_loglik_coop_kernel(const GgpDevForest F, const GgpFwdArgs A) {
     GgpMathTables& T = *reinterpret_cast<GgpMathTables*>(ggp_smem);
     __shared__ double sp[GGP_NP * (PRED ? GGP_COOP_SEG_SMEM : 1)];   // LIK: the vector's parameters; PRED: the first parameter sets
     __shared__ int s_steps[NG * GGP_COOP_ROLES];
@@ -195,7 +196,7 @@ __global__ void __launch_bounds__(GGP_COOP_BLOCK(NG), NG == 1 ? 3 : 4 / NG) ggp_
 // passes with the sign-flipped parameters (mean_cov_model_r, :191-198).
 // ------------------------------------------------------------------------------------------------
 template <int NG, bool GS>
-__global__ void __launch_bounds__(GGP_COOP_BLOCK(NG), NG == 1 ? 3 : 4 / NG) ggp_backward_coop_kernel(const GgpDevForest F, const GgpBwdArgs A) {
+__global__ void __launch_bounds__(GGP_COOP_BLOCK(NG), NG == 1 ? 3 : (NG <= 4 ? 4 / NG : 1)) ggp_backward_coop_kernel(const GgpDevForest F, const GgpBwdArgs A) {
     GgpMathTables& T = *reinterpret_cast<GgpMathTables*>(ggp_smem);
     __shared__ int s_steps[NG * GGP_COOP_ROLES];
     __shared__ double sp[GGP_NP * GGP_COOP_SEG_SMEM];

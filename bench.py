@@ -218,6 +218,10 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; this implementation has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    # stdout carries exactly one JSON line: native libraries that print there (NCCL's version banner) go to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = _lib.load()
@@ -365,7 +369,8 @@ def run_ours(args):
                                         args.cpu_sample_trees, sub.n_ctp, dt,
                                         "reference mean_cov_model.h + Faddeeva.cc (oracle/_ref) inside the oracle's filter loop" if use_ref
                                         else "oracle port"), "loglik": ll_cpu}
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     forest.close()
     if world > 1:
         dist.destroy_process_group()

@@ -353,3 +353,29 @@ def test_random_forests_all_passes_bitwise(seed):
     bm, bc = ggp.api.backward_cell_state(f)
     assert same_bits(bm, o.cell_mean) and same_bits(bc.reshape(-1, 16), o.cell_cov)
     f.close()
+
+
+@pytest.mark.gpu
+def test_full_size_predictions_properties():
+    """BASELINE.json config 3 at scale (scaled noise + binomial division, -p): 4 000 trees x 6 generations (252 000 cells,
+    ~5 M cell-timepoints, 2.4 GB of outputs) checked through size-independent properties: every prediction finite with
+    positive variances, run-to-run bitwise determinism, and bit-exact agreement with the oracle on a 30-tree sample
+    (the init statistics being those of the whole forest), for all three outputs"""
+    P = ggp.PARAMS_SCALED_BINOMIAL
+    d = ggp.simulate_forest(4000, 6, noise_model="scaled", division_model="binomial", seed=20261018)
+    f = ggp.Forest(d)
+    pr = ggp.prediction_forward_backward(f, [P])
+    for k in ("forward", "backward", "prediction"):
+        assert np.isfinite(pr[k][0]).all() and np.isfinite(pr[k][1]).all()
+        assert (np.diagonal(pr[k][1], axis1=1, axis2=2) > 0).all()
+    again = ggp.prediction_forward_backward(f, [P], forward=False, backward=False)
+    assert same_bits(again["prediction"][0], pr["prediction"][0]) and same_bits(again["prediction"][1], pr["prediction"][1])
+    # the smoothed variances never exceed the filtered ones by more than rounding (information only adds)
+    vf = np.diagonal(pr["forward"][1], axis1=1, axis2=2)[:, :2]
+    vs = np.diagonal(pr["prediction"][1], axis1=1, axis2=2)[:, :2]
+    assert (vs <= vf * (1 + 1e-6)).mean() > 0.999
+    sub, cells, ctp = d.subset(d.roots()[777:807])
+    ref = Oracle(sub).predictions([P])
+    for k in ("forward", "backward", "prediction"):
+        assert same_bits(pr[k][0][ctp], ref[k][0]) and same_bits(pr[k][1][ctp], ref[k][1]), k
+    f.close()

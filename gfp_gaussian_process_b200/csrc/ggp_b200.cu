@@ -109,6 +109,8 @@ struct ggp_forest {
     double last_ms = 0.0;
     int64_t last_launches = 0;
     int64_t state_budget_bytes = (int64_t)8 << 30;
+    int n_sm = 148;
+    int walk_blocks_per_sm = 4;   // joints walkers resident per SM (register-limited); GGP_B200_WALK_BLOCKS overrides
 
     GgpDevForest dev() const {
         GgpDevForest F;
@@ -206,6 +208,9 @@ int ggp_forest_create(const ggp_forest_desc* d, ggp_forest** out) {
         f->legacy_loglik = lg && lg[0] == '1';
         if (const char* m = getenv("GGP_B200_NG4_MIN")) f->coop_ng4_min_groups = atoll(m);
         if (const char* m = getenv("GGP_B200_COOP_VARIANT")) f->coop_variant = atoi(m);
+        if (const char* m = getenv("GGP_B200_WALK_BLOCKS")) f->walk_blocks_per_sm = std::max(1, atoi(m));
+        int n_sm = 0;
+        if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, f->device) == cudaSuccess && n_sm > 0) f->n_sm = n_sm;
     }
 
     cudaStream_t s = nullptr;

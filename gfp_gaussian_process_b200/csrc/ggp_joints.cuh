@@ -12,10 +12,14 @@
 // point k it passes (one mean_cov_model + one cross_cov_model each time) and keeps 8x8 Eigen matrices on
 // the heap.  Here the two quantities that depend on a single point only — the first joint
 // J0(k) = P(z_{k+1}, z_k | D_k) and the transformed conditional — are computed ONCE per cell-timepoint by a
-// first kernel (ggp_ctp_joint_prep: one propagation step with cross covariance per point) and cached in HBM;
-// a second kernel gives one thread to every start point, walks forward in time and depth-first into both
-// daughters with the 8-dim Gaussian in registers/local memory and an explicit stack of pending daughter
-// branches, and appends the joints it emits to a sparse list.
+// first kernel (ggp_ctp_joint_prep: one propagation step with cross covariance per point) and cached in HBM,
+// together with the two other per-point quantities every passing walk would recompute: the inverse of the
+// conditional's F and the backward prediction divided by the prior.  A second, persistent kernel walks the
+// start points: a thread takes the next start point from a device counter, walks forward in time and
+// depth-first into both daughters with the 8-dim Gaussian in registers/local memory and an explicit stack of
+// pending daughter branches, appends the joints it emits to a sparse list, and takes the next start point when
+// its walk ends - the walk is one flat loop, one point per iteration, so the lanes of a warp stay on the
+// step body together whatever the cell boundaries and walk lengths are.
 // Eigen semantics kept: dynamic inverses = partial-pivot LU (also the 2x2 of
 // include_measurement, which inverts a MatrixXd), dynamic products coefficient-wise left to right, matrix *
 // vector = column-major GEMV (four columns at a time, remaining columns one by one).
@@ -28,7 +32,10 @@ struct GgpAffine { double a[4]; double F[16]; double A[16]; };   // N(y | a + F 
 struct GgpGauss8 { double m[8]; double C[64]; };
 struct GgpSep { GgpGauss4 marg; GgpAffine cond; };
 
-#define GGP_JOINT_PREP 108   // doubles cached per ctp: J0 (8 + 64) then the conditional (4 + 16 + 16)
+#define GGP_JOINT_PREP 144   // doubles cached per ctp: J0 (8 + 64), the conditional (4 + 16 + 16), F^-1 (16), backward / prior (4 + 16)
+#define GGP_JP_COND 72
+#define GGP_JP_FINV 108
+#define GGP_JP_BW 124
 
 // C = op(A) * op(B), 4x4, coefficient-wise, inner sum left to right
 template <bool TA, bool TB>
@@ -117,18 +124,18 @@ GGP_HD void ggp_flip_xy(const GgpGauss8& J, GgpGauss8& R) {
 }
 
 // Gaussian::multiply (Gaussians.h:42-49)
-GGP_HD void ggp_gauss_multiply(const GgpGauss4& n1, const GgpGauss4& n2, GgpGauss4& out) {
+GGP_HD void ggp_gauss_multiply(const GgpGauss4& n1, const double* __restrict__ m2, const double* __restrict__ C2, GgpGauss4& out) {
     double S[16], Si[16], C2Si[16], C1Si[16], a[4], b[4];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) S[i] = n1.C[i] + n2.C[i];
+    for (int i = 0; i < 16; ++i) S[i] = n1.C[i] + C2[i];
     ggp_inv_lu<4>(S, Si);
-    ggp_mm4<false, false>(n2.C, Si, C2Si);
+    ggp_mm4<false, false>(C2, Si, C2Si);
     ggp_mm4<false, false>(n1.C, Si, C1Si);
     ggp_gemv4(C2Si, n1.m, a);
-    ggp_gemv4(C1Si, n2.m, b);
+    ggp_gemv4(C1Si, m2, b);
 #pragma unroll
     for (int i = 0; i < 4; ++i) out.m[i] = a[i] + b[i];
-    ggp_mm4<false, false>(C1Si, n2.C, out.C);
+    ggp_mm4<false, false>(C1Si, C2, out.C);
 }
 
 // Affine_gaussian::transform() (Gaussians.h:71-81): N(y | a + F x, A) -> N(x | a' + F' y, A')
@@ -166,31 +173,34 @@ GGP_HD void ggp_include_measurement(GgpGauss8& J, double D00, double D11, double
         for (int j = 0; j < 8; ++j) J.C[8 * i + j] = J.C[8 * i + j] - (T0[i] * K0[j] + T1[i] * K1[j]);
 }
 
-// next_joint (correlation_tree.h:426-454): P(z_{k+1}, z_n | D_{k+1}) x P(z_{k+2} | z_{k+1}, D_{k+1}) -> P(z_{k+2}, z_n | D_{k+1})
-GGP_HD void ggp_next_joint(const GgpGauss8& J, const GgpAffine& cond, GgpGauss8& out) {
-    GgpSep sep;
-    ggp_separate(J, sep);
+// next_joint (correlation_tree.h:426-454): P(z_{k+1}, z_n | D_{k+1}) x P(z_{k+2} | z_{k+1}, D_{k+1}) -> P(z_{k+2}, z_n | D_{k+1}).
+// sep = seperate_gaussian of the joint after include_measurement (shared with incorporate_backward_prob, which
+// separates the same joint); c = the cached block of the point: cond.a [4], cond.F [16], cond.A [16], cond.F^-1 [16]
+GGP_HD void ggp_next_joint(const GgpSep& sep, const double* __restrict__ c, GgpGauss8& out) {
+    const double* __restrict__ ca = c;
+    const double* __restrict__ cF = c + 4;
+    const double* __restrict__ cA = c + 20;
+    const double* __restrict__ Fi = c + 36;
     // calc_x / calc_X / calc_Y (correlation_tree.h:403-415)
     double S[16], Si[16], ASi[16], CSi[16], u[4], v[4];
     GgpAffine NX;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) S[i] = sep.marg.C[i] + cond.A[i];
+    for (int i = 0; i < 16; ++i) S[i] = sep.marg.C[i] + cA[i];
     ggp_inv_lu<4>(S, Si);
-    ggp_mm4<false, false>(cond.A, Si, ASi);
+    ggp_mm4<false, false>(cA, Si, ASi);
     ggp_mm4<false, false>(sep.marg.C, Si, CSi);
     ggp_gemv4(ASi, sep.marg.m, u);
-    ggp_gemv4(CSi, cond.a, v);
+    ggp_gemv4(CSi, ca, v);
 #pragma unroll
     for (int i = 0; i < 4; ++i) NX.a[i] = u[i] + v[i];
-    ggp_mm4<false, false>(CSi, cond.F, NX.F);
-    ggp_mm4<false, false>(CSi, cond.A, NX.A);
+    ggp_mm4<false, false>(CSi, cF, NX.F);
+    ggp_mm4<false, false>(CSi, cA, NX.A);
     // G.transform(marginal.m) (Gaussians.h:83-87) with G = (cond.a, cond.F, marginal.C + cond.A)
     GgpGauss4 nm;
     {
-        double Fi[16], d[4], FiA[16];
-        ggp_inv_lu<4>(cond.F, Fi);
+        double d[4], FiA[16];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) d[i] = sep.marg.m[i] - cond.a[i];
+        for (int i = 0; i < 4; ++i) d[i] = sep.marg.m[i] - ca[i];
         ggp_gemv4(Fi, d, nm.m);
         ggp_mm4<false, false>(Fi, S, FiA);
         ggp_mm4<false, true>(FiA, Fi, nm.C);
@@ -211,19 +221,11 @@ GGP_HD void ggp_next_joint(const GgpGauss8& J, const GgpAffine& cond, GgpGauss8&
     ggp_to_joint(nm, nc, out);
 }
 
-// incorporate_backward_prob (correlation_tree.h:457-482); mb/Cb = stored backward prediction at the point
-GGP_HD void ggp_incorporate_backward(const GgpGauss8& J, const double* __restrict__ mb, const double* __restrict__ Cb,
-                                     const double* __restrict__ p, GgpGauss8& out) {
-    GgpSep sep;
-    ggp_separate(J, sep);
-    GgpGauss4 bw;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) bw.m[i] = mb[i];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) bw.C[i] = Cb[i];
-    ggp_divide_by_prior(bw.m, bw.C, p);
+// incorporate_backward_prob (correlation_tree.h:457-482); bw = the backward prediction at the point already
+// divided by the prior (divide_by_prior depends on the point only: cached by the preparation), mean [4] then cov [16]
+GGP_HD void ggp_incorporate_backward(const GgpSep& sep, const double* __restrict__ bw, GgpGauss8& out) {
     GgpGauss4 marg;
-    ggp_gauss_multiply(sep.marg, bw, marg);
+    ggp_gauss_multiply(sep.marg, bw, bw + 4, marg);
     ggp_to_joint(marg, sep.cond, out);
 }
 
@@ -242,7 +244,9 @@ GGP_HD bool ggp_crosscov_small(const GgpGauss8& J, double tol) {
 // per-ctp preparation: J0(k) = P(z_{k+1}, z_k | D_k) (consecutive_joint, correlation_tree.h:325-357, or
 // consecutive_joint_cell_division :160-238 at a cell's last point) and the transformed conditional
 // (consecutive_conditional :360-396 / _cell_division :241-319), from the forward posterior at k.
-// prep = [J0.m 8][J0.C 64][cond.a 4][cond.F 16][cond.A 16]; nothing is written for the last point of a leaf.
+// prep = [J0.m 8][J0.C 64][cond.a 4][cond.F 16][cond.A 16][cond.F^-1 16][bw.m 4][bw.C 16]; bw = the backward
+// prediction at k divided by the prior (incorporate_backward_prob's first step, correlation_tree.h:466-468);
+// only bw is written for the last point of a leaf.
 // ------------------------------------------------------------------------------------------------
 struct GgpJointArgs {
     const double* params;    // [n_seg][11]
@@ -259,8 +263,9 @@ struct GgpJointArgs {
     long long* row_ctp;
     long long* col_ctp;
     double* rec44;
-    double* stack;           // [n_starts][stack_depth][72] pending daughter branches
-    int32_t* stack_slot;     // [n_starts][stack_depth]
+    unsigned long long* next_row;   // start points handed out so far (relative to row_begin)
+    double* stack;           // [n_threads][stack_depth][72] pending daughter branches
+    int32_t* stack_slot;     // [n_threads][stack_depth]
     int stack_depth;
 };
 
@@ -272,8 +277,22 @@ GGP_HD void ggp_ctp_joint_prep(const GgpDevForest& F, const GgpJointArgs& A, int
     const int t = (int)(k - off);
     const bool last = (t == n - 1);
     const int d1 = F.s_d1[slot];
-    if (last && d1 < 0) return;   // joints starting at / passing a leaf's last point go nowhere
     const double* p = A.params + GGP_NP * F.seg[k];
+    double* out = A.prep + (int64_t)GGP_JOINT_PREP * k;
+    {
+        GgpGauss4 bw;
+        const double* b = A.bwd + 20 * k;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) bw.m[i] = b[i];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) bw.C[i] = b[4 + i];
+        ggp_divide_by_prior(bw.m, bw.C, p);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) out[GGP_JP_BW + i] = bw.m[i];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) out[GGP_JP_BW + 4 + i] = bw.C[i];
+    }
+    if (last && d1 < 0) return;   // joints starting at / passing a leaf's last point go nowhere
     const double* f = A.fwd + 20 * k;
     double mean1[4], cov1[16];
 #pragma unroll
@@ -365,15 +384,16 @@ GGP_HD void ggp_ctp_joint_prep(const GgpDevForest& F, const GgpJointArgs& A, int
             ggp_affine_transform(c, cond);
         }
     }
-    double* out = A.prep + (int64_t)GGP_JOINT_PREP * k;
+    double Fi[16];
+    ggp_inv_lu<4>(cond.F, Fi);   // next_joint's G.transform inverts the conditional's F at every pass (Gaussians.h:83-87)
 #pragma unroll
     for (int i = 0; i < 8; ++i) out[i] = J0.m[i];
 #pragma unroll
     for (int i = 0; i < 64; ++i) out[8 + i] = J0.C[i];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) out[72 + i] = cond.a[i];
+    for (int i = 0; i < 4; ++i) out[GGP_JP_COND + i] = cond.a[i];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) { out[76 + i] = cond.F[i]; out[92 + i] = cond.A[i]; }
+    for (int i = 0; i < 16; ++i) { out[GGP_JP_COND + 4 + i] = cond.F[i]; out[GGP_JP_COND + 20 + i] = cond.A[i]; out[GGP_JP_FINV + i] = Fi[i]; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -408,84 +428,119 @@ GGP_HD void ggp_store_joint(double* __restrict__ dst, const GgpGauss8& J) {
     for (int i = 0; i < 64; ++i) dst[8 + i] = J.C[i];
 }
 
-GGP_HD void ggp_start_point_joints(const GgpDevForest& F, const GgpJointArgs& A, int64_t row, int64_t start_index) {
-    const int slot0 = A.ctp_slot[row];
-    const int n0 = (int)(row - F.s_off[slot0]);
-    const bool at_division = (n0 == F.s_n[slot0] - 1);
-    if (at_division && F.s_d1[slot0] < 0 && F.s_d2[slot0] < 0) return;   // last point of a leaf: empty row
-    double* stack = A.stack + (int64_t)start_index * A.stack_depth * 72;
-    int32_t* stack_slot = A.stack_slot + (int64_t)start_index * A.stack_depth;
-    int sp = 0;
+GGP_HD int64_t ggp_next_start_point(const GgpJointArgs& A) {
+#if defined(__CUDA_ARCH__)
+    return A.row_begin + (int64_t)atomicAdd(A.next_row, 1ull);
+#else
+    return A.row_begin + (int64_t)(*A.next_row)++;
+#endif
+}
+
+// Walks start points [row_begin, row_end) handed out by A.next_row until none is left.  `lane` selects this
+// thread's stack of pending daughter branches.
+GGP_HD void ggp_walk_start_points(const GgpDevForest& F, const GgpJointArgs& A, int64_t lane) {
+    double* stack = A.stack + lane * A.stack_depth * 72;
+    int32_t* stack_slot = A.stack_slot + lane * A.stack_depth;
     GgpGauss8 J, comb;
-    ggp_load_joint(A.prep + (int64_t)GGP_JOINT_PREP * row, J);
-    int slot = slot0;
-    int t;   // index of the point the joint's first half refers to, inside `slot`
-    if (!at_division) {
-        t = n0 + 1;
-    } else {
-        // consecutive_joint_cell_division needs daughter1 (correlation_tree.h:606-612); both daughters start from it
-        if (F.s_d1[slot0] < 0) return;
-        if (F.s_d2[slot0] >= 0) {
-            ggp_store_joint(stack, J);
-            stack_slot[0] = F.s_d2[slot0];
-            sp = 1;
-        }
-        slot = F.s_d1[slot0];
-        t = 0;
-    }
+    int64_t row = 0, off = 0;
+    int slot = 0, t = 0, n = 0, sp = 0, d1 = -1;
+    double stale_g = 0.0;
+    bool walking = false;
     for (;;) {
-        // ---- calc_joint_distributions on `slot` from index t (correlation_tree.h:499-558) ----
-        const int64_t off = F.s_off[slot];
-        const int n = F.s_n[slot];
-        const double stale_g = A.bstate[20 * (int64_t)slot + 1];   // MOMAdata::mean(1) left by the backward pass
-        bool stop = false;
-        for (; t < n; ++t) {
-            const int64_t k = off + t;
-            const double* p = A.params + GGP_NP * F.seg[k];
-            const double D11 = F.model.noise_scaled ? p[8] * (stale_g + F.model.fp_auto) : p[8];
-            ggp_include_measurement(J, p[7], D11, F.x[k], F.g[k]);
-            ggp_incorporate_backward(J, A.bwd + 20 * k, A.bwd + 20 * k + 4, p, comb);
-            if (ggp_crosscov_small(comb, A.tol)) { stop = true; break; }
-            ggp_emit_joint(A, row, k, comb);
-            if (t < n - 1 || F.s_d1[slot] >= 0) {
-                const double* c = A.prep + (int64_t)GGP_JOINT_PREP * k + 72;
-                GgpAffine cond;
-                for (int i = 0; i < 4; ++i) cond.a[i] = c[i];
-                for (int i = 0; i < 16; ++i) { cond.F[i] = c[4 + i]; cond.A[i] = c[20 + i]; }
-                GgpGauss8 nx;
-                ggp_next_joint(J, cond, nx);
-                J = nx;
-            }
-        }
-        if (!stop) {
-            // into the daughters (joint_distributions_recr, correlation_tree.h:566-585): daughter1 first
-            const int d1 = F.s_d1[slot], d2 = F.s_d2[slot];
-            if (d1 >= 0) {
-                if (d2 >= 0 && sp < A.stack_depth) {
-                    ggp_store_joint(stack + (int64_t)sp * 72, J);
-                    stack_slot[sp] = d2;
-                    ++sp;
+        // ---- settle on the next point to process: next start point when the walk has ended, daughters or a
+        //      pending branch at the end of a cell (joint_distributions_recr, correlation_tree.h:566-585) ----
+        while (!walking || t >= n) {
+            bool enter = false;
+            if (!walking) {
+                row = ggp_next_start_point(A);
+                if (row >= A.row_end) return;
+                const int slot0 = A.ctp_slot[row];
+                const int n0 = (int)(row - F.s_off[slot0]);
+                const bool at_division = (n0 == F.s_n[slot0] - 1);
+                // the last point of a leaf has an empty row; consecutive_joint_cell_division needs daughter1
+                // (correlation_tree.h:606-612), both daughters start from it
+                if (at_division && F.s_d1[slot0] < 0) continue;
+                ggp_load_joint(A.prep + (int64_t)GGP_JOINT_PREP * row, J);
+                sp = 0;
+                walking = true;
+                if (!at_division) {
+                    slot = slot0;
+                    t = n0 + 1;
+                } else {
+                    if (F.s_d2[slot0] >= 0) {
+                        ggp_store_joint(stack, J);
+                        stack_slot[0] = F.s_d2[slot0];
+                        sp = 1;
+                    }
+                    slot = F.s_d1[slot0];
+                    t = 0;
                 }
-                slot = d1;
-                t = 0;
-                continue;
+                enter = true;
+            } else {
+                const int d2 = F.s_d2[slot];
+                if (d1 >= 0) {   // daughter1 first, daughter2 continues from the same joint later
+                    if (d2 >= 0 && sp < A.stack_depth) {
+                        ggp_store_joint(stack + (int64_t)sp * 72, J);
+                        stack_slot[sp] = d2;
+                        ++sp;
+                    }
+                    slot = d1;
+                    t = 0;
+                    enter = true;
+                } else if (d2 >= 0) {   // daughter2 without daughter1: unreachable with build_cell_genealogy
+                    slot = d2;
+                    t = 0;
+                    enter = true;
+                } else if (sp > 0) {
+                    --sp;
+                    ggp_load_joint(stack + (int64_t)sp * 72, J);
+                    slot = stack_slot[sp];
+                    t = 0;
+                    enter = true;
+                } else {
+                    walking = false;
+                }
             }
-            if (d2 >= 0) {   // daughter2 without daughter1: it keeps whatever joint it had; unreachable with build_cell_genealogy
-                slot = d2;
-                t = 0;
-                continue;
+            if (enter) {
+                off = F.s_off[slot];
+                n = F.s_n[slot];
+                d1 = F.s_d1[slot];
+                stale_g = A.bstate[20 * (int64_t)slot + 1];   // MOMAdata::mean(1) left by the backward pass
             }
         }
-        if (sp == 0) break;
-        --sp;
-        ggp_load_joint(stack + (int64_t)sp * 72, J);
-        slot = stack_slot[sp];
-        t = 0;
+        // ---- one point of calc_joint_distributions (correlation_tree.h:499-558) ----
+        const int64_t k = off + t;
+        const double* p = A.params + GGP_NP * F.seg[k];
+        const double* c = A.prep + (int64_t)GGP_JOINT_PREP * k;
+        const double D11 = F.model.noise_scaled ? p[8] * (stale_g + F.model.fp_auto) : p[8];
+        ggp_include_measurement(J, p[7], D11, F.x[k], F.g[k]);
+        GgpSep sep;
+        ggp_separate(J, sep);
+        ggp_incorporate_backward(sep, c + GGP_JP_BW, comb);
+        if (ggp_crosscov_small(comb, A.tol)) {
+            // this branch ends here; a pending daughter2 branch continues
+            if (sp > 0) {
+                --sp;
+                ggp_load_joint(stack + (int64_t)sp * 72, J);
+                slot = stack_slot[sp];
+                t = 0;
+                off = F.s_off[slot];
+                n = F.s_n[slot];
+                d1 = F.s_d1[slot];
+                stale_g = A.bstate[20 * (int64_t)slot + 1];
+            } else {
+                walking = false;
+            }
+            continue;
+        }
+        ggp_emit_joint(A, row, k, comb);
+        if (t < n - 1 || d1 >= 0) ggp_next_joint(sep, c + GGP_JP_COND, J);
+        ++t;
     }
 }
 
 #if defined(__CUDACC__)
-// ---- kernels: one thread per ctp (preparation), one thread per start point (walk) ----
+// ---- kernels: one thread per ctp (preparation), persistent threads taking start points from a counter (walk) ----
 __global__ void __launch_bounds__(GGP_BLOCK) ggp_joint_prep_kernel(const GgpDevForest F, const GgpJointArgs A) {
     GgpMathTables& T = *reinterpret_cast<GgpMathTables*>(ggp_smem);
     ggp_stage_tables(&T);
@@ -494,9 +549,8 @@ __global__ void __launch_bounds__(GGP_BLOCK) ggp_joint_prep_kernel(const GgpDevF
     ggp_ctp_joint_prep(F, A, k, &T, ggp_thread_scratch());
 }
 
-__global__ void __launch_bounds__(64) ggp_joint_walk_kernel(const GgpDevForest F, const GgpJointArgs A) {
-    const int64_t i = (int64_t)blockIdx.x * 64 + threadIdx.x;
-    if (A.row_begin + i >= A.row_end) return;
-    ggp_start_point_joints(F, A, A.row_begin + i, i);
+#define GGP_WALK_BLOCK 64
+__global__ void __launch_bounds__(GGP_WALK_BLOCK) ggp_joint_walk_kernel(const GgpDevForest F, const GgpJointArgs A) {
+    ggp_walk_start_points(F, A, (int64_t)blockIdx.x * GGP_WALK_BLOCK + threadIdx.x);
 }
 #endif

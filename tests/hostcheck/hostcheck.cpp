@@ -274,7 +274,7 @@ int hc_predict_coop(const ggp_forest_desc* d, const double* params, int n_seg, d
     return 0;
 }
 
-// joints on the host: predict, per-ctp preparation, then one walk per start point (row), rows in ctp order;
+// joints on the host: predict, per-ctp preparation, then one walker over every start point (row), rows in ctp order;
 // returns the number of joints, writes at most cap (unsorted inside a row: emission order)
 long long hc_joints(const ggp_forest_desc* d, const double* params, int n_seg, double tol, long long cap, long long* row, long long* col, double* rec44) {
     GgpLayout L;
@@ -291,13 +291,14 @@ long long hc_joints(const ggp_forest_desc* d, const double* params, int n_seg, d
     for (int64_t s = L.n_cells - 1; s >= 0; --s) ggp_cell_backward(F, B, (int)s, &g_tables, S);
     std::vector<double> prep((size_t)GGP_JOINT_PREP * L.n_ctp), stack((size_t)72 * (L.n_gen + 1));
     std::vector<int32_t> stack_slot(L.n_gen + 1);
-    unsigned long long count = 0;
+    unsigned long long count = 0, next_row = 0;
     GgpJointArgs J{};
     J.params = params; J.fwd = fwd.data(); J.bwd = bwd.data(); J.bstate = bstate.data(); J.prep = prep.data();
     J.ctp_slot = L.ctp_slot.data(); J.tol = tol; J.cap = cap; J.count = &count; J.row_ctp = row; J.col_ctp = col; J.rec44 = rec44;
     J.stack = stack.data(); J.stack_slot = stack_slot.data(); J.stack_depth = L.n_gen + 1;
     for (int64_t k = 0; k < L.n_ctp; ++k) ggp_ctp_joint_prep(F, J, k, &g_tables, S);
-    for (int64_t k = 0; k < L.n_ctp; ++k) ggp_start_point_joints(F, J, k, 0);
+    J.next_row = &next_row; J.row_begin = 0; J.row_end = L.n_ctp;
+    ggp_walk_start_points(F, J, 0);   // one walker takes every start point in turn
     return (long long)count;
 }
 }

@@ -110,7 +110,7 @@ struct ggp_forest {
     int64_t last_launches = 0;
     int64_t state_budget_bytes = (int64_t)8 << 30;
     int n_sm = 148;
-    int walk_blocks_per_sm = 4;   // joints walkers resident per SM (register-limited); GGP_B200_WALK_BLOCKS overrides
+    int walk_blocks_per_sm = 1;   // joints walker blocks (256 threads) resident per SM (register-limited); GGP_B200_WALK_BLOCKS overrides
 
     GgpDevForest dev() const {
         GgpDevForest F;

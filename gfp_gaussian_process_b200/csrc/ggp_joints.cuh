@@ -428,6 +428,16 @@ GGP_HD void ggp_store_joint(double* __restrict__ dst, const GgpGauss8& J) {
     for (int i = 0; i < 64; ++i) dst[8 + i] = J.C[i];
 }
 
+// All walkers of a block start each point together (device): the step body is ~7 000 instructions of straight-line
+// code, and warps spread over it each fetch it on their own.  Returns whether any walker of the block is still walking.
+GGP_HD bool ggp_walkers_align(bool walking) {
+#if defined(__CUDA_ARCH__)
+    return __syncthreads_or(walking) != 0;
+#else
+    return walking;
+#endif
+}
+
 GGP_HD int64_t ggp_next_start_point(const GgpJointArgs& A) {
 #if defined(__CUDA_ARCH__)
     return A.row_begin + (int64_t)atomicAdd(A.next_row, 1ull);
@@ -445,15 +455,15 @@ GGP_HD void ggp_walk_start_points(const GgpDevForest& F, const GgpJointArgs& A, 
     int64_t row = 0, off = 0;
     int slot = 0, t = 0, n = 0, sp = 0, d1 = -1;
     double stale_g = 0.0;
-    bool walking = false;
+    bool walking = false, drained = false;
     for (;;) {
         // ---- settle on the next point to process: next start point when the walk has ended, daughters or a
         //      pending branch at the end of a cell (joint_distributions_recr, correlation_tree.h:566-585) ----
-        while (!walking || t >= n) {
+        while (!drained && (!walking || t >= n)) {
             bool enter = false;
             if (!walking) {
                 row = ggp_next_start_point(A);
-                if (row >= A.row_end) return;
+                if (row >= A.row_end) { drained = true; break; }
                 const int slot0 = A.ctp_slot[row];
                 const int n0 = (int)(row - F.s_off[slot0]);
                 const bool at_division = (n0 == F.s_n[slot0] - 1);
@@ -508,6 +518,8 @@ GGP_HD void ggp_walk_start_points(const GgpDevForest& F, const GgpJointArgs& A, 
                 stale_g = A.bstate[20 * (int64_t)slot + 1];   // MOMAdata::mean(1) left by the backward pass
             }
         }
+        if (!ggp_walkers_align(walking)) return;
+        if (!walking) continue;   // out of start points; the block's other walkers are still busy
         // ---- one point of calc_joint_distributions (correlation_tree.h:499-558) ----
         const int64_t k = off + t;
         const double* p = A.params + GGP_NP * F.seg[k];
@@ -549,8 +561,8 @@ __global__ void __launch_bounds__(GGP_BLOCK) ggp_joint_prep_kernel(const GgpDevF
     ggp_ctp_joint_prep(F, A, k, &T, ggp_thread_scratch());
 }
 
-#define GGP_WALK_BLOCK 64
-__global__ void __launch_bounds__(GGP_WALK_BLOCK) ggp_joint_walk_kernel(const GgpDevForest F, const GgpJointArgs A) {
+#define GGP_WALK_BLOCK 256
+__global__ void __launch_bounds__(GGP_WALK_BLOCK, 1) ggp_joint_walk_kernel(const GgpDevForest F, const GgpJointArgs A) {
     ggp_walk_start_points(F, A, (int64_t)blockIdx.x * GGP_WALK_BLOCK + threadIdx.x);
 }
 #endif

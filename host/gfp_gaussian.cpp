@@ -491,6 +491,25 @@ void run_prediction_segments(Session& S, Forest& F, std::vector<ParameterSet>& l
         }
 }
 
+const int64_t kJointRowBlock = 32768;   // start points per ggp_joints call
+
+// Records of the start points [r0, r1) in (row, col) order.  One library call when the buffers of the previous block
+// were large enough (they grow with the densest block seen), otherwise a second one with the exact size.
+void fetch_joints(ggp_forest* handle, const std::vector<double>& P, int n_seg, double tol, int64_t r0, int64_t r1,
+                  std::vector<int64_t>& row, std::vector<int64_t>& col, std::vector<double>& rec, int64_t& n) {
+    int64_t cap = (int64_t)std::min(row.size(), std::min(col.size(), rec.size() / 44));
+    if (cap < 64 * (r1 - r0)) {
+        cap = 64 * (r1 - r0);
+        row.resize(cap); col.resize(cap); rec.resize((size_t)cap * 44);
+    }
+    check(ggp_joints(handle, P.data(), n_seg, tol, r0, r1, cap, &n, row.data(), col.data(), rec.data()), "ggp_joints");
+    if (n > cap) {
+        cap = n + n / 8;
+        row.resize(cap); col.resize(cap); rec.resize((size_t)cap * 44);
+        check(ggp_joints(handle, P.data(), n_seg, tol, r0, r1, cap, &n, row.data(), col.data(), rec.data()), "ggp_joints");
+    }
+}
+
 void run_joint_distribution(Session& S, Forest& Fx, std::vector<ParameterSet>& list) {
     S.log << "-> joint posteriors\n";
     const LineageTable& T = Fx.table();
@@ -521,16 +540,14 @@ void run_joint_distribution(Session& S, Forest& Fx, std::vector<ParameterSet>& l
         for (int64_t k = 0; k < M; ++k) f << T.cell_id[cell_of[k]] << '_' << T.time[k] << std::string(k == M - 1 ? 43 : 44, ',');
         f << "\n";
     }
-    // rows are streamed in blocks like the reference streams lines
-    const int64_t block = 4096;
+    // rows are streamed in blocks like the reference streams lines (a block keeps every SM's walkers busy)
+    const int64_t block = kJointRowBlock;
     std::vector<int64_t> row, col;
     std::vector<double> rec;
     for (int64_t r0 = 0; r0 < M; r0 += block) {
         const int64_t r1 = std::min(M, r0 + block);
         int64_t n = 0;
-        check(ggp_joints(handle, P.data(), (int32_t)list.size(), tol, r0, r1, 0, &n, nullptr, nullptr, nullptr), "ggp_joints");
-        row.resize(std::max<int64_t>(n, 1)); col.resize(std::max<int64_t>(n, 1)); rec.resize((size_t)std::max<int64_t>(n, 1) * 44);
-        check(ggp_joints(handle, P.data(), (int32_t)list.size(), tol, r0, r1, n, &n, row.data(), col.data(), rec.data()), "ggp_joints");
+        fetch_joints(handle, P, (int)list.size(), tol, r0, r1, row, col, rec, n);
         int64_t at = 0;
         for (int64_t r = r0; r < r1; ++r) {
             const int64_t c = cell_of[r];
@@ -588,13 +605,12 @@ void run_correlation(Session& S, Forest& Fx, std::vector<ParameterSet>& list) {
     src.marginal14 = [&](int64_t k) { return m14.data() + 14 * k; };
     src.joints_of_rows = [&](int64_t r0, int64_t r1, std::vector<int64_t>& row, std::vector<int64_t>& col, std::vector<double>& rec) {
         int64_t n = 0;
-        check(ggp_joints(handle, P.data(), (int32_t)list.size(), tol, r0, r1, 0, &n, nullptr, nullptr, nullptr), "ggp_joints");
-        row.assign(std::max<int64_t>(n, 1), -1); col.assign(std::max<int64_t>(n, 1), -1); rec.assign((size_t)std::max<int64_t>(n, 1) * 44, 0.0);
-        check(ggp_joints(handle, P.data(), (int32_t)list.size(), tol, r0, r1, n, &n, row.data(), col.data(), rec.data()), "ggp_joints");
+        row.resize(row.capacity()); col.resize(col.capacity());   // reuse what the previous block grew to
+        fetch_joints(handle, P, (int)list.size(), tol, r0, r1, row, col, rec, n);
         row.resize(n); col.resize(n);
     };
     CorrelationSet CS = make_correlation_set(S);
-    correlation_from_joints(CS, T.cell_id, T.parent_id, T.offset, T.time, src, S.args.count("normalize_time") > 0);
+    correlation_from_joints(CS, T.cell_id, T.parent_id, T.offset, T.time, src, S.args.count("normalize_time") > 0, kJointRowBlock);
     CS.finalize();
     const std::string outfile = prediction_base(S, list) + "_correlations.csv";
     S.log << "Outfile: " << outfile << "\n";

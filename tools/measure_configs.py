@@ -117,6 +117,27 @@ if "cfg5" in which:   # -j on a 100k-cell forest with two segments (sparse outpu
     for _ in range(3):
         _lib.check(lib.ggp_joints(f.handle, P.ctypes.data_as(_lib.c_double_p), 2, C.c_double(1e-10), 0, rows, 0, C.byref(cnt), None, None, None))
         walk_ms.append(f.last_kernel_ms)
+    # with records: walk + device sort into (row, col) order + copy into the caller's (pageable) arrays
+    capn = int(cnt.value)
+    hrow = np.empty(capn, dtype=np.int64); hcol = np.empty(capn, dtype=np.int64); hrec = np.empty((capn, 44))
+    hrec[:] = 0.0   # touch the pages
+    rec_s = []
+    for _ in range(2):
+        t = time.perf_counter()
+        _lib.check(lib.ggp_joints(f.handle, P.ctypes.data_as(_lib.c_double_p), 2, C.c_double(1e-10), 0, rows, capn, C.byref(cnt),
+                                  hrow.ctypes.data_as(_lib.c_int64_p), hcol.ctypes.data_as(_lib.c_int64_p), hrec.ctypes.data_as(_lib.c_double_p)))
+        rec_s.append(time.perf_counter() - t)
+    assert (np.diff(hrow) >= 0).all()
+    out(config="cfg5 -j with records: first %d start points, %d records (%.2f GB) into host arrays in (row, col) order" % (rows, capn, capn * 368 / 1e9),
+        wall_s=float(np.min(rec_s)), records_per_s=capn / float(np.min(rec_s)))
+    del hrow, hcol, hrec
+    all_ms = []
+    call = C.c_int64(0)
+    for _ in range(2):
+        _lib.check(lib.ggp_joints(f.handle, P.ctypes.data_as(_lib.c_double_p), 2, C.c_double(1e-10), 0, int(data.n_ctp), 0, C.byref(call), None, None, None))
+        all_ms.append(f.last_kernel_ms)
+    out(config="cfg5 -j 100k cells, 2 segments, tol 1e-10, every start point, count only", n_ctp=int(data.n_ctp), joints=int(call.value),
+        walk_ms=float(np.min(all_ms)), walk_joints_per_s=call.value / (np.min(all_ms) * 1e-3))
     out(config="cfg5 -j 100k cells, 2 segments, tol 1e-10 (first %d start points, count only)" % rows, n_cells=int(data.n_cells),
         n_ctp=int(data.n_ctp), predict_s=tp, joints=int(cnt.value), joints_per_start=cnt.value / rows, wall_s=dt, kernel_ms=first_ms,
         walk_ms=float(np.median(walk_ms)), joints_per_s=cnt.value / dt, walk_joints_per_s=cnt.value / (np.median(walk_ms) * 1e-3))

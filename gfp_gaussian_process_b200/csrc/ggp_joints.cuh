@@ -553,12 +553,16 @@ GGP_HD void ggp_walk_start_points(const GgpDevForest& F, const GgpJointArgs& A, 
 
 #if defined(__CUDACC__)
 // ---- kernels: one thread per ctp (preparation), persistent threads taking start points from a counter (walk) ----
+// resident blocks loop over the points and start every round together: the body is ~16 000 instructions of
+// straight-line code, warps that drift apart each fetch it on their own
 __global__ void __launch_bounds__(GGP_BLOCK) ggp_joint_prep_kernel(const GgpDevForest F, const GgpJointArgs A) {
     GgpMathTables& T = *reinterpret_cast<GgpMathTables*>(ggp_smem);
     ggp_stage_tables(&T);
-    const int64_t k = (int64_t)blockIdx.x * GGP_BLOCK + threadIdx.x;
-    if (k >= F.n_ctp) return;
-    ggp_ctp_joint_prep(F, A, k, &T, ggp_thread_scratch());
+    for (int64_t base = (int64_t)blockIdx.x * GGP_BLOCK; base < F.n_ctp; base += (int64_t)gridDim.x * GGP_BLOCK) {
+        __syncthreads();
+        const int64_t k = base + threadIdx.x;
+        if (k < F.n_ctp) ggp_ctp_joint_prep(F, A, k, &T, ggp_thread_scratch());
+    }
 }
 
 #define GGP_WALK_BLOCK 256

@@ -648,6 +648,18 @@ int ggp_fp64_peak(int32_t device, double* tflops_out) {
     return GGP_OK;
 }
 
+#ifdef GGP_PHASE_CLOCKS
+// profiling builds only: out[role][10] = clocks per (phase work / barrier wait) slot, see ggp_coop_kernels.cuh
+int ggp_debug_phase_clocks(unsigned long long* out, int reset) {
+    if (out) GGP_CUDA(cudaMemcpyFromSymbol(out, ggp_phase_clk, sizeof(ggp_phase_clk)));
+    if (reset) {
+        unsigned long long z[GGP_COOP_ROLES][10] = {};
+        GGP_CUDA(cudaMemcpyToSymbol(ggp_phase_clk, z, sizeof(z)));
+    }
+    return GGP_OK;
+}
+#endif
+
 }  // extern "C"
 
 #include "ggp_joints_host.inc"

@@ -32,6 +32,32 @@ __device__ __forceinline__ void ggp_cp_async8(double* smem_dst, const double* gm
 }
 __device__ __forceinline__ void ggp_cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// Profiling aid (never in the shipped build): -DGGP_PHASE_CLOCKS accumulates, per role, the SM clocks spent inside each
+// phase and waiting at each barrier of the likelihood step (ggp_debug_phase_clocks reads them; tools/phase_clocks.py).
+#ifdef GGP_PHASE_CLOCKS
+__device__ unsigned long long ggp_phase_clk[GGP_COOP_ROLES][10];
+// per-warp accumulators in shared memory, flushed once per block (contended global atomics inside the loop would show up
+// in role 0's cp.async wait)
+#define GGP_CLK_DECL                                                      \
+    __shared__ unsigned long long s_clk[32][10];                          \
+    if (lane < 10) s_clk[warp][lane] = 0;                                 \
+    __syncwarp();                                                         \
+    long long clk_last = clock64();
+#define GGP_CLK_MARK(slot)                                                \
+    if (!PRED && lane == 0) {                                             \
+        const long long now = clock64();                                  \
+        s_clk[warp][slot] += (unsigned long long)(now - clk_last);        \
+        clk_last = now;                                                   \
+    }
+#define GGP_CLK_FLUSH                                                     \
+    __syncwarp();                                                         \
+    if (!PRED && lane < 10) atomicAdd(&ggp_phase_clk[role][lane], s_clk[warp][lane]);
+#else
+#define GGP_CLK_DECL
+#define GGP_CLK_MARK(slot)
+#define GGP_CLK_FLUSH
+#endif
+
 // PRED = false: likelihood (likelihood.h:36-103, one parameter vector per blockIdx.y); PRED = true: prediction_forward
 // (predictions.h:93-150): parameters by segment, the posterior of every point stored to A.out_fwd.
 template <int NG, bool GS, bool STEP_ALIGN = false, bool PRED = false>
@@ -130,10 +156,13 @@ __global__ void __launch_bounds__(GGP_COOP_BLOCK(NG), NG == 1 ? 3 : (NG <= 4 ? 4
     int seg_from = (PRED && active) ? F.seg[from] : 0;
     int seg_at = (PRED && steps > 0) ? F.seg[off + t + 1] : 0;
     ggp_coop_sync<GS>(group);
+    bool pend = false;   // LIK, role 0: a log-evidence term is pending in GGP_CS_LL
+    GGP_CLK_DECL
     for (int it = 0; it < max_steps; ++it) {
         const bool live = it < steps;
         const int in = GGP_CS_IN + 4 * (it & 1);
         if (GS && STEP_ALIGN) __syncthreads();   // re-align the block's groups once per step (instruction-cache sharing)
+        GGP_CLK_MARK(0)
         const int seg_next = (PRED && it + 1 < steps) ? F.seg[off + t + 2] : 0;
         if (role == 0 && it + 1 < steps) {
             const int64_t at = off + t + 2;
@@ -142,6 +171,13 @@ __global__ void __launch_bounds__(GGP_COOP_BLOCK(NG), NG == 1 ? 3 : (NG <= 4 ? 4
             ggp_cp_async8(&S[nx + 1], F.time + at - 1);
             ggp_cp_async8(&S[nx + 2], F.x + at);
             ggp_cp_async8(&S[nx + 3], F.g + at);
+        }
+        // LIK: the previous step's log-evidence term, left pending by phase 3 (ggp_coop.cuh), finished here where role 0 has slack
+        if (!PRED && role == 0 && pend) {
+            const double ll = ggp_coop_ll_deferred(GGP_SLOTS_REF(S), &T);
+            own = own + ll;
+            if (ll != ll) GGP_NAN_MIN(A.nan_key + A.v0 + v, F.s_dfs0[slot] + t);
+            pend = false;
         }
         const double* pt = p;   // parameters of the point the step arrives at
         if (PRED && live) {
@@ -155,27 +191,37 @@ __global__ void __launch_bounds__(GGP_COOP_BLOCK(NG), NG == 1 ? 3 : (NG <= 4 ? 4
             ggp_coop_run_phase(0, role, S, PRED ? ggp_ou(p, false) : ou_lik, dt, &T, ge_same);
             prev_seg = seg_from;
         }
+        GGP_CLK_MARK(1)
         ggp_coop_sync<GS>(group);
+        GGP_CLK_MARK(2)
 #pragma unroll
         for (int ph = 1; ph < GGP_COOP_PHASES; ++ph) {
             if (live) ggp_coop_run_phase(ph, role, S, PRED ? ggp_ou(p, false) : ou_lik, 0.0, &T, false,
                                          PRED ? (seg_staged ? s_gl3[seg_from] : GGP_NO_GL3) : gl3_lik);
+            GGP_CLK_MARK(1 + 2 * ph)
             ggp_coop_sync<GS>(group);
+            GGP_CLK_MARK(2 + 2 * ph)
         }
         if (live) {
             const double ll = PRED ? ggp_coop_ph3_pred<false>(role, S, t < 0, p, pt, S[in + 2], S[in + 3], F.model, &T, A.out_fwd + 20 * (off + t + 1))
-                                   : ggp_coop_ph3(role, S, t < 0, p, S[in + 2], S[in + 3], F.model, &T);
+                                   : ggp_coop_ph3<true>(role, S, t < 0, p, S[in + 2], S[in + 3], F.model, &T);
+            (void)ll;
             ++t;
             from = off + t;
             seg_from = seg_at;
             seg_at = seg_next;
-            if (!PRED && role == 0) {
-                own = own + ll;
-                if (ll != ll) GGP_NAN_MIN(A.nan_key + A.v0 + v, F.s_dfs0[slot] + t);
-            }
+            if (!PRED && role == 0) pend = true;
         }
         if (role == 0) ggp_cp_async_wait();
+        GGP_CLK_MARK(7)
         ggp_coop_sync<GS>(group);
+        GGP_CLK_MARK(8)
+    }
+    GGP_CLK_FLUSH
+    if (!PRED && role == 0 && pend) {   // the last point's term
+        const double ll = ggp_coop_ll_deferred(GGP_SLOTS_REF(S), &T);
+        own = own + ll;
+        if (ll != ll) GGP_NAN_MIN(A.nan_key + A.v0 + v, F.s_dfs0[slot] + t);
     }
     if (active && (F.s_d1[slot] >= 0 || F.s_d2[slot] >= 0)) {
         for (int k = role; k < 14; k += GGP_COOP_ROLES) A.state[k * vstride + vbase + slot] = S[GGP_CS_ST + k];

@@ -52,13 +52,16 @@ GGP_HD GgpMeas ggp_measure(const GgpState& s, double c10, double x, double g, do
     return m;
 }
 
-// -1/2 r^T Si r - 1/2 log det S - 2 log 2pi (likelihood.h:26-32; the constant is as written there)
-GGP_HD double ggp_log_evidence(const GgpMeas& m, const GgpMathTables* __restrict__ M) {
+// -1/2 r^T Si r - 1/2 log det S - 2 log 2pi (likelihood.h:26-32; the constant is as written there), in two pieces so that
+// the cooperative likelihood step can evaluate the second one (a serial chain: division, log) off its critical path.
+GGP_HD double ggp_log_evidence_quad(const GgpMeas& m) {
     double r0 = (-0.5 * m.xg0) * m.Si00 + (-0.5 * m.xg1) * m.Si10;
     double r1 = (-0.5 * m.xg0) * m.Si01 + (-0.5 * m.xg1) * m.Si11;
-    double a = r0 * m.xg0 + r1 * m.xg1;
+    return r0 * m.xg0 + r1 * m.xg1;
+}
+GGP_HD double ggp_log_evidence_finish(double a, double S00, double S01, double S10, double S11, const GgpMathTables* __restrict__ M) {
     // determinant of the dynamic-size copy: partial-pivot LU
-    double p00 = m.S00, p01 = m.S01, p10 = m.S10, p11 = m.S11, sign = 1.0;
+    double p00 = S00, p01 = S01, p10 = S10, p11 = S11, sign = 1.0;
     if (fabs(p10) > fabs(p00)) {
         double t0 = p00, t1 = p01;
         p00 = p10; p01 = p11; p10 = t0; p11 = t1;
@@ -68,6 +71,9 @@ GGP_HD double ggp_log_evidence(const GgpMeas& m, const GgpMathTables* __restrict
     p11 = p11 - p10 * p01;
     double det = sign * (p00 * p11);
     return a - 0.5 * ggp_log(det, M) - GGP_TWO_LOG_2PI;
+}
+GGP_HD double ggp_log_evidence(const GgpMeas& m, const GgpMathTables* __restrict__ M) {
+    return ggp_log_evidence_finish(ggp_log_evidence_quad(m), m.S00, m.S01, m.S10, m.S11, M);
 }
 
 // Kalman update of mean and upper triangle (predictions.h:84-89).  If full16 != nullptr the complete

@@ -122,21 +122,25 @@ int hc_loglik_coop(const ggp_forest_desc* d, const double* params, int n_vec, do
                 t = -1;
                 from = F.s_off[parent] + F.s_n[parent] - 1;
             }
+            bool pend = false;   // as in the kernel: phase 3 leaves the log-evidence term pending, the next phase 0 (or the tail) finishes it
+            auto finish_pending = [&]() {
+                const double ll = ggp_coop_ll_deferred(GGP_SLOTS_REF(S), &g_tables);
+                own = own + ll;
+                if (ll != ll) GGP_NAN_MIN(&nan, F.s_dfs0[slot] + t);
+                pend = false;
+            };
             while (t + 1 < n) {
                 const double dt = F.time[off + t + 1] - F.time[from];
+                if (pend) finish_pending();
                 for (int ph = 0; ph < GGP_COOP_PHASES; ++ph)
                     for (int role = 0; role < GGP_COOP_ROLES; ++role) ggp_coop_run_phase(ph, role, S, ggp_ou(p, false), dt, &g_tables);
                 const int64_t at = off + t + 1;
-                double ll = 0.0;
-                for (int role = 0; role < GGP_COOP_ROLES; ++role) {
-                    const double r = ggp_coop_ph3(role, S, t < 0, p, F.x[at], F.g[at], F.model, &g_tables);
-                    if (role == 0) ll = r;
-                }
+                for (int role = 0; role < GGP_COOP_ROLES; ++role) ggp_coop_ph3<true>(role, S, t < 0, p, F.x[at], F.g[at], F.model, &g_tables);
                 ++t;
                 from = at;
-                own = own + ll;
-                if (ll != ll) GGP_NAN_MIN(&nan, F.s_dfs0[slot] + t);
+                pend = true;
             }
+            if (pend) finish_pending();
             for (int k = 0; k < 14; ++k) state[k * L.n_cells + slot] = S[GGP_CS_ST + k];
             out_cell_ll[(int64_t)v * L.n_cells + F.s_cell[slot]] = own;
         }

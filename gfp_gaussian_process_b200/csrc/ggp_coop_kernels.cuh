@@ -34,6 +34,9 @@ __device__ __forceinline__ void ggp_cp_async_wait() { asm volatile("cp.async.wai
 
 // Profiling aid (never in the shipped build): -DGGP_PHASE_CLOCKS accumulates, per role, the SM clocks spent inside each
 // phase and waiting at each barrier of the likelihood step (ggp_debug_phase_clocks reads them; tools/phase_clocks.py).
+#ifndef GGP_OPT_MERGE_BAR
+#define GGP_OPT_MERGE_BAR 1
+#endif
 #ifdef GGP_PHASE_CLOCKS
 __device__ unsigned long long ggp_phase_clk[GGP_COOP_ROLES][10];
 // per-warp accumulators in shared memory, flushed once per block (contended global atomics inside the loop would show up
@@ -45,8 +48,10 @@ __device__ unsigned long long ggp_phase_clk[GGP_COOP_ROLES][10];
     long long clk_last = clock64();
 #define GGP_CLK_MARK(slot)                                                \
     if (!PRED && lane == 0) {                                             \
+        volatile unsigned long long* q = &s_clk[warp][slot];              \
+        const unsigned long long acc = *q;   /* a memory operation first: BAR.SYNC.DEFER_BLOCKING lets the clock read run ahead of the barrier */ \
         const long long now = clock64();                                  \
-        s_clk[warp][slot] += (unsigned long long)(now - clk_last);        \
+        *q = acc + (unsigned long long)(now - clk_last);                  \
         clk_last = now;                                                   \
     }
 #define GGP_CLK_FLUSH                                                     \
@@ -214,9 +219,11 @@ __global__ void __launch_bounds__(GGP_COOP_BLOCK(NG), NG == 1 ? 3 : (NG <= 4 ? 4
         }
         if (role == 0) ggp_cp_async_wait();
         GGP_CLK_MARK(7)
-        ggp_coop_sync<GS>(group);
+        // end of step: with step alignment the block barrier at the top of the next iteration is this barrier too
+        if (!(GGP_OPT_MERGE_BAR && NG > 1 && GS && STEP_ALIGN)) ggp_coop_sync<GS>(group);
         GGP_CLK_MARK(8)
     }
+    if (GGP_OPT_MERGE_BAR && NG > 1 && GS && STEP_ALIGN) ggp_coop_sync<GS>(group);   // the last step's posterior, read below by all roles
     GGP_CLK_FLUSH
     if (!PRED && role == 0 && pend) {   // the last point's term
         const double ll = ggp_coop_ll_deferred(GGP_SLOTS_REF(S), &T);

@@ -87,6 +87,15 @@ struct ggp_forest {
     cudaStream_t copy_stream = nullptr;
     std::vector<cudaEvent_t> chunk_ready;
     cudaEvent_t compute_done = nullptr;
+    // streamed evaluation: chunk k's launches run on chunk_stream[k] (the last chunk on the handle's stream), so that the
+    // small early generations of one chunk (a few blocks, latency bound) run beside the large late generations of another
+    std::vector<cudaStream_t> chunk_stream;
+    std::vector<cudaEvent_t> chunk_done;
+    cudaEvent_t eval_start = nullptr;
+    bool chunk_streams = true;            // GGP_B200_CHUNK_STREAMS=0: every chunk on the handle's stream
+    bool timeline = false;                // GGP_B200_TIMELINE=1: chunk events carry timestamps; ggp_loglik prints landing / start / end of every chunk
+    cudaEvent_t tl_upload0 = nullptr;
+    std::vector<cudaEvent_t> tl_begin, tl_end;
     bool upload_pending = false;
     const double* h_inline_params = nullptr;   // set by ggp_loglik for the duration of one streamed evaluation
     int64_t coop_ng4_min_groups = 4 * 148 * 2;   // launches with at least this many 32-cell groups use 4 groups per block
@@ -167,9 +176,24 @@ int ggp_forest_create(const ggp_forest_desc* d, ggp_forest** out) {
     if (!d || !out) return fail(GGP_ERR_BAD_ARG, "null argument");
     *out = nullptr;
     ggp_forest* f = new ggp_forest();
-    int32_t want_chunks = d->n_ctp >= (int64_t)2000000 ? 3 : 1;   // measured on cfg2: 2 -> 9.7 ms, 3 -> 9.0 ms, 4 -> 9.7 ms, 8 -> 11.7 ms end to end (1 chunk: 11.6 ms)
+    // measured on cfg2, end to end per step: one stream for all chunks 1 -> 11.6 ms, 2 -> 9.7, 3 -> 9.0 (8.47 with the final
+    // kernels), 4 -> 9.7, 8 -> 11.7; one stream per chunk (chunk_stream): 3 -> 8.25, 6 -> 7.95, 8 / 12 -> 7.93; the copy
+    // alone takes 5.5 ms (55 GB/s), the evaluation keeps up with it at ~80 % of its resident rate (gpurun_out timeline:
+    // every chunk's launches take ~2.2 ms, three chunks in flight), small first chunks do not help
+    int32_t want_chunks = d->n_ctp >= (int64_t)2000000 ? 6 : 1;
     if (const char* m = getenv("GGP_B200_UPLOAD_CHUNKS")) want_chunks = atoi(m);
-    const std::string why = f->L.build(d, want_chunks);
+    std::vector<double> fractions;   // GGP_B200_CHUNK_FRACTIONS=a,b,c,...: relative chunk sizes (A/B measurements)
+    if (const char* m = getenv("GGP_B200_CHUNK_FRACTIONS")) {
+        for (const char* q = m; *q;) {
+            char* end = nullptr;
+            const double v = strtod(q, &end);
+            if (end == q) break;
+            if (v > 0.0) fractions.push_back(v);
+            q = (*end == ',') ? end + 1 : end;
+        }
+        if (!fractions.empty()) want_chunks = (int32_t)fractions.size();
+    }
+    const std::string why = f->L.build(d, want_chunks, fractions.empty() ? nullptr : fractions.data());
     if (!why.empty()) {
         delete f;
         return fail(GGP_ERR_BAD_ARG, why);
@@ -236,8 +260,25 @@ int ggp_forest_create(const ggp_forest_desc* d, ggp_forest** out) {
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&f->copy_stream, cudaStreamNonBlocking);
     f->chunk_ready.assign(L.n_chunks, nullptr);
-    for (int k = 0; k < L.n_chunks && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&f->chunk_ready[k], cudaEventDisableTiming);
+    f->timeline = getenv("GGP_B200_TIMELINE") != nullptr;
+    for (int k = 0; k < L.n_chunks && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&f->chunk_ready[k], f->timeline ? cudaEventDefault : cudaEventDisableTiming);
+    if (f->timeline) {
+        f->tl_begin.assign(L.n_chunks, nullptr);
+        f->tl_end.assign(L.n_chunks, nullptr);
+        cudaEventCreate(&f->tl_upload0);
+        for (int k = 0; k < L.n_chunks; ++k) { cudaEventCreate(&f->tl_begin[k]); cudaEventCreate(&f->tl_end[k]); }
+    }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&f->compute_done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&f->eval_start, cudaEventDisableTiming);
+    if (const char* m = getenv("GGP_B200_CHUNK_STREAMS")) f->chunk_streams = atoi(m) != 0;
+    if (L.n_chunks > 1) {
+        f->chunk_stream.assign(L.n_chunks - 1, nullptr);
+        f->chunk_done.assign(L.n_chunks - 1, nullptr);
+        for (int k = 0; k + 1 < L.n_chunks && e == cudaSuccess; ++k) {
+            e = cudaStreamCreateWithFlags(&f->chunk_stream[k], cudaStreamNonBlocking);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&f->chunk_done[k], cudaEventDisableTiming);
+        }
+    }
     if (e == cudaSuccess) e = cudaEventCreate(&f->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&f->ev1);
     if (e != cudaSuccess) {
@@ -263,6 +304,9 @@ void ggp_forest_destroy(ggp_forest* f) {
     f->w_nan.release();
     for (cudaEvent_t ev : f->chunk_ready) if (ev) cudaEventDestroy(ev);
     if (f->compute_done) cudaEventDestroy(f->compute_done);
+    if (f->eval_start) cudaEventDestroy(f->eval_start);
+    for (cudaEvent_t ev : f->chunk_done) if (ev) cudaEventDestroy(ev);
+    for (cudaStream_t st : f->chunk_stream) if (st) cudaStreamDestroy(st);
     if (f->copy_stream) cudaStreamDestroy(f->copy_stream);
     if (f->ev0) cudaEventDestroy(f->ev0);
     if (f->ev1) cudaEventDestroy(f->ev1);
@@ -283,6 +327,7 @@ int ggp_forest_upload_series(ggp_forest* f, const double* time, const double* lo
     // likelihood evaluation starts on a chunk's trees as soon as that chunk has landed (enqueue_loglik)
     GGP_CUDA(cudaEventRecord(f->compute_done, f->stream));
     GGP_CUDA(cudaStreamWaitEvent(f->copy_stream, f->compute_done, 0));
+    if (f->timeline) GGP_CUDA(cudaEventRecord(f->tl_upload0, f->copy_stream));
     for (int k = 0; k < f->L.n_chunks; ++k) {
         const int64_t c0 = f->L.ctp_chunk_start[k];
         const size_t b = (size_t)(f->L.ctp_chunk_start[k + 1] - c0) * sizeof(double);
@@ -356,8 +401,15 @@ int enqueue_loglik(ggp_forest* f, const double* d_params, int32_t n_vec, double*
             const size_t cnt = (size_t)vc * n_partial;
             ggp_fill64_kernel<<<(unsigned)std::min<size_t>((cnt + 255) / 256, 1184), 256, 0, f->stream>>>(reinterpret_cast<unsigned long long*>(f->w_partial.p), 0ull, cnt);
         }
+        const bool multi = streamed && f->chunk_streams;
+        if (multi) GGP_CUDA(cudaEventRecord(f->eval_start, f->stream));
         for (int k = 0; k < (streamed ? K : 1); ++k) {
-            if (streamed) GGP_CUDA(cudaStreamWaitEvent(f->stream, f->chunk_ready[k], 0));
+            // stream of this chunk's launches: its own (behind everything enqueued on the handle's stream so far), the
+            // handle's for the last chunk
+            const cudaStream_t ks = (multi && k + 1 < K) ? f->chunk_stream[k] : f->stream;
+            if (multi && k + 1 < K) GGP_CUDA(cudaStreamWaitEvent(ks, f->eval_start, 0));
+            if (streamed) GGP_CUDA(cudaStreamWaitEvent(ks, f->chunk_ready[k], 0));
+            if (streamed && f->timeline) GGP_CUDA(cudaEventRecord(f->tl_begin[k], ks));
             for (int g = 0; g < f->n_gen; ++g) {
                 const int64_t* row = f->L.gen_chunk_start.data() + (size_t)g * (K + 1);
                 GgpFwdArgs A{};
@@ -378,28 +430,31 @@ int enqueue_loglik(ggp_forest* f, const double* d_params, int32_t n_vec, double*
                 A.out_fwd = nullptr;
                 const int gx = grid_of(A.n_slots);
                 if (g == 0 && d_carry && f->legacy_loglik)
-                    ggp_forward_kernel<false, true><<<dim3(gx, 1), GGP_BLOCK, GGP_SMEM_BYTES, f->stream>>>(F, A);
+                    ggp_forward_kernel<false, true><<<dim3(gx, 1), GGP_BLOCK, GGP_SMEM_BYTES, ks>>>(F, A);
                 else if (g == 0 && d_carry)
-                    ggp_loglik_chain_coop_kernel<<<dim3(grid_of_coop(A.n_slots), 1), GGP_COOP_BLOCK(1), GGP_COOP_SMEM_BYTES_CHAIN, f->stream>>>(F, A);
+                    ggp_loglik_chain_coop_kernel<<<dim3(grid_of_coop(A.n_slots), 1), GGP_COOP_BLOCK(1), GGP_COOP_SMEM_BYTES_CHAIN, ks>>>(F, A);
                 else if (f->legacy_loglik)
-                    ggp_forward_kernel<false, false><<<dim3(gx, vc), GGP_BLOCK, GGP_SMEM_BYTES, f->stream>>>(F, A);
+                    ggp_forward_kernel<false, false><<<dim3(gx, vc), GGP_BLOCK, GGP_SMEM_BYTES, ks>>>(F, A);
                 else if ((int64_t)grid_of_coop(A.n_slots) * vc >= f->coop_ng4_min_groups) {
                     const int ng = grid_of_coop(A.n_slots);
                     if (f->coop_variant == 2)
-                        ggp_loglik_coop_kernel<2, false><<<dim3((ng + 1) / 2, vc), GGP_COOP_BLOCK(2), GGP_COOP_SMEM_BYTES(2), f->stream>>>(F, A);
+                        ggp_loglik_coop_kernel<2, false><<<dim3((ng + 1) / 2, vc), GGP_COOP_BLOCK(2), GGP_COOP_SMEM_BYTES(2), ks>>>(F, A);
                     else if (f->coop_variant == 5)
-                        ggp_loglik_coop_kernel<5, true, true><<<dim3((ng + 4) / 5, vc), GGP_COOP_BLOCK(5), GGP_COOP_SMEM_BYTES(5), f->stream>>>(F, A);
+                        ggp_loglik_coop_kernel<5, true, true><<<dim3((ng + 4) / 5, vc), GGP_COOP_BLOCK(5), GGP_COOP_SMEM_BYTES(5), ks>>>(F, A);
                     else if (f->coop_variant == 4)
-                        ggp_loglik_coop_kernel<4, true, true><<<dim3((ng + 3) / 4, vc), GGP_COOP_BLOCK(4), GGP_COOP_SMEM_BYTES(4), f->stream>>>(F, A);
+                        ggp_loglik_coop_kernel<4, true, true><<<dim3((ng + 3) / 4, vc), GGP_COOP_BLOCK(4), GGP_COOP_SMEM_BYTES(4), ks>>>(F, A);
                     else if (f->coop_variant == 3)
-                        ggp_loglik_coop_kernel<4, true><<<dim3((ng + 3) / 4, vc), GGP_COOP_BLOCK(4), GGP_COOP_SMEM_BYTES(4), f->stream>>>(F, A);
+                        ggp_loglik_coop_kernel<4, true><<<dim3((ng + 3) / 4, vc), GGP_COOP_BLOCK(4), GGP_COOP_SMEM_BYTES(4), ks>>>(F, A);
                     else
-                        ggp_loglik_coop_kernel<4, false><<<dim3((ng + 3) / 4, vc), GGP_COOP_BLOCK(4), GGP_COOP_SMEM_BYTES(4), f->stream>>>(F, A);
+                        ggp_loglik_coop_kernel<4, false><<<dim3((ng + 3) / 4, vc), GGP_COOP_BLOCK(4), GGP_COOP_SMEM_BYTES(4), ks>>>(F, A);
                 } else
-                    ggp_loglik_coop_kernel<1, false><<<dim3(grid_of_coop(A.n_slots), vc), GGP_COOP_BLOCK(1), GGP_COOP_SMEM_BYTES(1), f->stream>>>(F, A);
+                    ggp_loglik_coop_kernel<1, false><<<dim3(grid_of_coop(A.n_slots), vc), GGP_COOP_BLOCK(1), GGP_COOP_SMEM_BYTES(1), ks>>>(F, A);
                 ++f->last_launches;
             }
+            if (streamed && f->timeline) GGP_CUDA(cudaEventRecord(f->tl_end[k], ks));
+            if (multi && k + 1 < K) GGP_CUDA(cudaEventRecord(f->chunk_done[k], ks));
         }
+        if (multi) for (int k = 0; k + 1 < K; ++k) GGP_CUDA(cudaStreamWaitEvent(f->stream, f->chunk_done[k], 0));
         ggp_reduce_kernel<<<vc, 256, 0, f->stream>>>(f->w_partial.p, n_partial, d_out + v0);
         ++f->last_launches;
     }
@@ -454,6 +509,17 @@ int ggp_loglik(ggp_forest* f, const double* params, int32_t n_vec, double* root_
     float ms = 0.f;
     GGP_CUDA(cudaEventElapsedTime(&ms, f->ev0, f->ev1));
     f->last_ms = ms;
+    if (f->timeline && f->tl_upload0 && cudaEventQuery(f->tl_begin[0]) == cudaSuccess && cudaEventQuery(f->tl_upload0) == cudaSuccess) {
+        for (int k = 0; k < f->L.n_chunks; ++k) {
+            float a = 0, b = 0, c = 0;
+            if (cudaEventElapsedTime(&a, f->tl_upload0, f->chunk_ready[k]) != cudaSuccess || cudaEventElapsedTime(&b, f->tl_upload0, f->tl_begin[k]) != cudaSuccess ||
+                cudaEventElapsedTime(&c, f->tl_upload0, f->tl_end[k]) != cudaSuccess) { cudaGetLastError(); break; }
+            fprintf(stderr, "[ggp timeline] chunk %d: landed %.2f ms, launches begin %.2f, end %.2f\n", k, a, b, c);
+        }
+        float e = 0;
+        if (cudaEventElapsedTime(&e, f->tl_upload0, f->ev1) == cudaSuccess) fprintf(stderr, "[ggp timeline] reduce done %.2f ms\n", e);
+        cudaGetLastError();
+    }
     bool any_nan = false;
     for (int32_t v = 0; v < n_vec; ++v) {
         int64_t cell = -1, t = -1;

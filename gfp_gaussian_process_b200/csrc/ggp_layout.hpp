@@ -61,7 +61,8 @@ struct GgpLayout {
     }
 
     // returns "" on success, else the reason (the reference throws std::invalid_argument)
-    std::string build(const ggp_forest_desc* d, int32_t want_chunks = 1) {
+    // chunk_fractions (optional, want_chunks entries, any positive scale): relative sizes of the upload chunks
+    std::string build(const ggp_forest_desc* d, int32_t want_chunks = 1, const double* chunk_fractions = nullptr) {
         if (!d) return "null descriptor";
         if (d->n_cells <= 0 || d->n_ctp <= 0 || !d->cell_offset || !d->parent || !d->time || !d->log_length || !d->fp)
             return "empty forest or missing array";
@@ -117,7 +118,17 @@ struct GgpLayout {
         // upload chunks and the chunk of every cell (= of its tree)
         n_chunks = std::max<int32_t>(1, std::min<int64_t>(want_chunks, d->n_ctp));
         ctp_chunk_start.assign(n_chunks + 1, 0);
-        for (int32_t k = 0; k <= n_chunks; ++k) ctp_chunk_start[k] = d->n_ctp * k / n_chunks;
+        if (chunk_fractions && n_chunks == want_chunks) {
+            double tot = 0.0, acc = 0.0;
+            for (int32_t k = 0; k < n_chunks; ++k) tot += chunk_fractions[k];
+            for (int32_t k = 0; k < n_chunks; ++k) {
+                ctp_chunk_start[k] = std::max<int64_t>(k ? ctp_chunk_start[k - 1] : 0, (int64_t)((double)d->n_ctp * (acc / tot)));
+                acc += chunk_fractions[k];
+            }
+            ctp_chunk_start[n_chunks] = d->n_ctp;
+        } else {
+            for (int32_t k = 0; k <= n_chunks; ++k) ctp_chunk_start[k] = d->n_ctp * k / n_chunks;
+        }
         std::vector<int32_t> chunk(N, 0);
         if (n_chunks > 1) {
             std::vector<int32_t> root_of(N, -1), order(N);

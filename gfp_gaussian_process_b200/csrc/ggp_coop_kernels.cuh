@@ -34,6 +34,12 @@ __device__ __forceinline__ void ggp_cp_async_wait() { asm volatile("cp.async.wai
 
 // Profiling aid (never in the shipped build): -DGGP_PHASE_CLOCKS accumulates, per role, the SM clocks spent inside each
 // phase and waiting at each barrier of the likelihood step (ggp_debug_phase_clocks reads them; tools/phase_clocks.py).
+#ifndef GGP_OPT_STAGGER_NS
+#define GGP_OPT_STAGGER_NS 0
+#endif
+#ifndef GGP_OPT_ALIGN_PERIOD
+#define GGP_OPT_ALIGN_PERIOD 4
+#endif
 #ifndef GGP_OPT_MERGE_BAR
 #define GGP_OPT_MERGE_BAR 1
 #endif
@@ -161,12 +167,18 @@ __global__ void __launch_bounds__(GGP_COOP_BLOCK(NG), NG == 1 ? 3 : (NG <= 4 ? 4
     int seg_from = (PRED && active) ? F.seg[from] : 0;
     int seg_at = (PRED && steps > 0) ? F.seg[off + t + 1] : 0;
     ggp_coop_sync<GS>(group);
+#if GGP_OPT_STAGGER_NS > 0
+    // free-running groups (no step alignment): the second half of the block's groups starts half a step late, so that the
+    // two halves sit in different phases (FP64-heavy slot loops vs shared-memory-heavy role code) from then on
+    if (!PRED && NG > 1 && GS && !STEP_ALIGN && group >= NG / 2) __nanosleep(GGP_OPT_STAGGER_NS);
+#endif
     bool pend = false;   // LIK, role 0: a log-evidence term is pending in GGP_CS_LL
     GGP_CLK_DECL
     for (int it = 0; it < max_steps; ++it) {
         const bool live = it < steps;
         const int in = GGP_CS_IN + 4 * (it & 1);
-        if (GS && STEP_ALIGN) __syncthreads();   // re-align the block's groups once per step (instruction-cache sharing)
+        // re-align the block's groups every GGP_OPT_ALIGN_PERIOD steps (instruction-cache sharing: the groups then fetch the same code at about the same time)
+        if (GS && STEP_ALIGN && (GGP_OPT_ALIGN_PERIOD == 1 || it % GGP_OPT_ALIGN_PERIOD == 0)) __syncthreads();
         GGP_CLK_MARK(0)
         const int seg_next = (PRED && it + 1 < steps) ? F.seg[off + t + 2] : 0;
         if (role == 0 && it + 1 < steps) {
@@ -220,10 +232,10 @@ __global__ void __launch_bounds__(GGP_COOP_BLOCK(NG), NG == 1 ? 3 : (NG <= 4 ? 4
         if (role == 0) ggp_cp_async_wait();
         GGP_CLK_MARK(7)
         // end of step: with step alignment the block barrier at the top of the next iteration is this barrier too
-        if (!(GGP_OPT_MERGE_BAR && NG > 1 && GS && STEP_ALIGN)) ggp_coop_sync<GS>(group);
+        if (!(GGP_OPT_MERGE_BAR && GGP_OPT_ALIGN_PERIOD == 1 && NG > 1 && GS && STEP_ALIGN)) ggp_coop_sync<GS>(group);
         GGP_CLK_MARK(8)
     }
-    if (GGP_OPT_MERGE_BAR && NG > 1 && GS && STEP_ALIGN) ggp_coop_sync<GS>(group);   // the last step's posterior, read below by all roles
+    if (GGP_OPT_MERGE_BAR && GGP_OPT_ALIGN_PERIOD == 1 && NG > 1 && GS && STEP_ALIGN) ggp_coop_sync<GS>(group);   // the last step's posterior, read below by all roles
     GGP_CLK_FLUSH
     if (!PRED && role == 0 && pend) {   // the last point's term
         const double ll = ggp_coop_ll_deferred(GGP_SLOTS_REF(S), &T);

@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(GGP_COOP_BLOCK(NG), NG == 1 ? 3 : (NG <= 4 ? 4
     for (int it = 0; it < max_steps; ++it) {
         const bool live = it < steps;
         const int in = GGP_CS_IN + 4 * (it & 1);
-        if (GS && NG > 1) __syncthreads();
+        if (GS && NG > 1 && (GGP_OPT_ALIGN_PERIOD == 1 || it % GGP_OPT_ALIGN_PERIOD == 0)) __syncthreads();
         const int64_t at = off + t - 1;   // the point this step arrives at
         const int seg_next = it + 1 < steps ? F.seg[at - 1] : 0;
         if (role == 0 && it + 1 < steps) {

@@ -26,6 +26,9 @@
 // groups per block of the prediction passes: 3 (384 threads, up to 170 registers) keeps their larger per-thread state
 // (segment lookups, output pointers) out of local memory; with 4 groups the 128-register cap spills loop-carried values
 // and, with the L1 carve-out almost entirely shared memory, every reload goes to L2
+#ifndef GGP_PRED_UNI_NG
+#define GGP_PRED_UNI_NG 4   // groups per block of the one-segment prediction kernels (uniform parameters)
+#endif
 #ifndef GGP_PRED_NG
 #define GGP_PRED_NG 3
 #endif
@@ -92,6 +95,7 @@ struct ggp_forest {
     std::vector<cudaStream_t> chunk_stream;
     std::vector<cudaEvent_t> chunk_done;
     cudaEvent_t eval_start = nullptr;
+    bool pred_uni = true;                 // GGP_B200_PRED_UNI=0: one-segment data sets use the general prediction kernels
     bool chunk_streams = true;            // GGP_B200_CHUNK_STREAMS=0: every chunk on the handle's stream
     bool timeline = false;                // GGP_B200_TIMELINE=1: chunk events carry timestamps; ggp_loglik prints landing / start / end of every chunk
     cudaEvent_t tl_upload0 = nullptr;
@@ -156,6 +160,8 @@ cudaError_t opt_in_smem() {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(ggp_loglik_coop_kernel<5, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GGP_COOP_SMEM_BYTES(5));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(ggp_loglik_coop_kernel<1, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GGP_COOP_SMEM_BYTES(1));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(ggp_loglik_coop_kernel<GGP_PRED_NG, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GGP_COOP_SMEM_BYTES(GGP_PRED_NG));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ggp_loglik_coop_kernel<GGP_PRED_UNI_NG, true, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GGP_COOP_SMEM_BYTES(GGP_PRED_UNI_NG));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ggp_backward_coop_kernel<GGP_PRED_UNI_NG, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GGP_COOP_SMEM_BYTES(GGP_PRED_UNI_NG));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(ggp_backward_coop_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GGP_COOP_SMEM_BYTES(1));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(ggp_backward_coop_kernel<GGP_PRED_NG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GGP_COOP_SMEM_BYTES(GGP_PRED_NG));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(ggp_loglik_chain_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GGP_COOP_SMEM_BYTES_CHAIN);
@@ -271,6 +277,7 @@ int ggp_forest_create(const ggp_forest_desc* d, ggp_forest** out) {
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&f->compute_done, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&f->eval_start, cudaEventDisableTiming);
     if (const char* m = getenv("GGP_B200_CHUNK_STREAMS")) f->chunk_streams = atoi(m) != 0;
+    if (const char* m = getenv("GGP_B200_PRED_UNI")) f->pred_uni = atoi(m) != 0;
     if (L.n_chunks > 1) {
         f->chunk_stream.assign(L.n_chunks - 1, nullptr);
         f->chunk_done.assign(L.n_chunks - 1, nullptr);
@@ -592,6 +599,8 @@ int ggp_predict(ggp_forest* f, const double* params, int32_t n_seg, double* out_
         const int ng = grid_of_coop(A.n_slots);
         if (f->legacy_loglik)
             ggp_forward_kernel<true, false><<<dim3(grid_of(A.n_slots), 1), GGP_BLOCK, GGP_SMEM_BYTES, s>>>(F, A);
+        else if (ng >= f->coop_ng4_min_groups && n_seg == 1 && f->pred_uni)
+            ggp_loglik_coop_kernel<GGP_PRED_UNI_NG, true, true, true, true><<<dim3((ng + GGP_PRED_UNI_NG - 1) / GGP_PRED_UNI_NG, 1), GGP_COOP_BLOCK(GGP_PRED_UNI_NG), GGP_COOP_SMEM_BYTES(GGP_PRED_UNI_NG), s>>>(F, A);
         else if (ng >= f->coop_ng4_min_groups)
             ggp_loglik_coop_kernel<GGP_PRED_NG, true, true, true><<<dim3((ng + GGP_PRED_NG - 1) / GGP_PRED_NG, 1), GGP_COOP_BLOCK(GGP_PRED_NG), GGP_COOP_SMEM_BYTES(GGP_PRED_NG), s>>>(F, A);
         else
@@ -610,6 +619,8 @@ int ggp_predict(ggp_forest* f, const double* params, int32_t n_seg, double* out_
         const int ng = grid_of_coop(B.n_slots);
         if (f->legacy_loglik)
             ggp_backward_kernel<<<grid_of(B.n_slots), GGP_BLOCK, GGP_SMEM_BYTES, s>>>(F, B);
+        else if (ng >= f->coop_ng4_min_groups && n_seg == 1 && f->pred_uni)
+            ggp_backward_coop_kernel<GGP_PRED_UNI_NG, true, true><<<(ng + GGP_PRED_UNI_NG - 1) / GGP_PRED_UNI_NG, GGP_COOP_BLOCK(GGP_PRED_UNI_NG), GGP_COOP_SMEM_BYTES(GGP_PRED_UNI_NG), s>>>(F, B);
         else if (ng >= f->coop_ng4_min_groups)
             ggp_backward_coop_kernel<GGP_PRED_NG, true><<<(ng + GGP_PRED_NG - 1) / GGP_PRED_NG, GGP_COOP_BLOCK(GGP_PRED_NG), GGP_COOP_SMEM_BYTES(GGP_PRED_NG), s>>>(F, B);
         else

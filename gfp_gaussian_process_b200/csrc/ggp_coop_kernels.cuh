@@ -71,8 +71,11 @@ __device__ unsigned long long ggp_phase_clk[GGP_COOP_ROLES][10];
 
 // PRED = false: likelihood (likelihood.h:36-103, one parameter vector per blockIdx.y); PRED = true: prediction_forward
 // (predictions.h:93-150): parameters by segment, the posterior of every point stored to A.out_fwd.
-template <int NG, bool GS, bool STEP_ALIGN = false, bool PRED = false>
+// UNI (PRED only): the data set has one segment, so the parameters are block-uniform like the likelihood's (no per-lane
+// parameter pointers, no segment look-ups: the registers those cost are what keeps the prediction passes at 3 groups)
+template <int NG, bool GS, bool STEP_ALIGN = false, bool PRED = false, bool UNI = false>
 __global__ void __launch_bounds__(GGP_COOP_BLOCK(NG), NG == 1 ? 3 : (NG <= 4 ? 4 / NG : 1)) ggp_loglik_coop_kernel(const GgpDevForest F, const GgpFwdArgs A) {
+    constexpr bool SEGS = PRED && !UNI;   // per-point parameter sets
     GgpMathTables& T = *reinterpret_cast<GgpMathTables*>(ggp_smem);
     __shared__ double sp[GGP_NP * (PRED ? GGP_COOP_SEG_SMEM : 1)];   // LIK: the vector's parameters; PRED: the first parameter sets
     __shared__ int s_steps[NG * GGP_COOP_ROLES];
@@ -102,12 +105,12 @@ __global__ void __launch_bounds__(GGP_COOP_BLOCK(NG), NG == 1 ? 3 : (NG <= 4 ? 4
         parent = F.s_parent[slot];
     }
     const int64_t vstride = (int64_t)A.v_count * F.n_cells, vbase = (int64_t)v * F.n_cells;
-    const int seg0 = (PRED && active) ? F.seg[off] : 0;
+    const int seg0 = (SEGS && active) ? F.seg[off] : 0;
     double own = 0.0;
     int t = 0;
     int64_t from = off;
     __syncthreads();   // sp
-    const double* p = PRED ? seg_params(seg0) : sp;
+    const double* p = SEGS ? seg_params(seg0) : sp;
     if (active) {
         if (parent < 0) {
             if (role == 0) {   // root: first update on the full matrix (predictions.h:63-82, likelihood.h:53-69)
@@ -164,8 +167,8 @@ __global__ void __launch_bounds__(GGP_COOP_BLOCK(NG), NG == 1 ? 3 : (NG <= 4 ? 4
         S[GGP_CS_IN + 3] = F.g[at];
     }
     // PRED: segment of the point a step leaves from / arrives at; the next step's is fetched one step ahead
-    int seg_from = (PRED && active) ? F.seg[from] : 0;
-    int seg_at = (PRED && steps > 0) ? F.seg[off + t + 1] : 0;
+    int seg_from = (SEGS && active) ? F.seg[from] : 0;
+    int seg_at = (SEGS && steps > 0) ? F.seg[off + t + 1] : 0;
     ggp_coop_sync<GS>(group);
 #if GGP_OPT_STAGGER_NS > 0
     // free-running groups (no step alignment): the second half of the block's groups starts half a step late, so that the
@@ -180,7 +183,7 @@ __global__ void __launch_bounds__(GGP_COOP_BLOCK(NG), NG == 1 ? 3 : (NG <= 4 ? 4
         // re-align the block's groups every GGP_OPT_ALIGN_PERIOD steps (instruction-cache sharing: the groups then fetch the same code at about the same time)
         if (GS && STEP_ALIGN && (GGP_OPT_ALIGN_PERIOD == 1 || it % GGP_OPT_ALIGN_PERIOD == 0)) __syncthreads();
         GGP_CLK_MARK(0)
-        const int seg_next = (PRED && it + 1 < steps) ? F.seg[off + t + 2] : 0;
+        const int seg_next = (SEGS && it + 1 < steps) ? F.seg[off + t + 2] : 0;
         if (role == 0 && it + 1 < steps) {
             const int64_t at = off + t + 2;
             const int nx = GGP_CS_IN + 4 * ((it + 1) & 1);
@@ -197,15 +200,15 @@ __global__ void __launch_bounds__(GGP_COOP_BLOCK(NG), NG == 1 ? 3 : (NG <= 4 ? 4
             pend = false;
         }
         const double* pt = p;   // parameters of the point the step arrives at
-        if (PRED && live) {
+        if (SEGS && live) {
             p = seg_params(seg_from);
             pt = seg_params(seg_at);
         }
         if (live) {
             const double dt = S[in + 0] - S[in + 1];
             // same dt (and parameters) as this cell's previous step: GGP_CS_GE still holds the elementary exponentials
-            const bool ge_same = role == 0 && it > 0 && dt == S[GGP_CS_K + GGP_K_T] && (!PRED || seg_from == prev_seg);
-            ggp_coop_run_phase(0, role, S, PRED ? ggp_ou(p, false) : ou_lik, dt, &T, ge_same);
+            const bool ge_same = role == 0 && it > 0 && dt == S[GGP_CS_K + GGP_K_T] && (!SEGS || seg_from == prev_seg);
+            ggp_coop_run_phase(0, role, S, SEGS ? ggp_ou(p, false) : ou_lik, dt, &T, ge_same);
             prev_seg = seg_from;
         }
         GGP_CLK_MARK(1)
@@ -213,7 +216,7 @@ __global__ void __launch_bounds__(GGP_COOP_BLOCK(NG), NG == 1 ? 3 : (NG <= 4 ? 4
         GGP_CLK_MARK(2)
 #pragma unroll
         for (int ph = 1; ph < GGP_COOP_PHASES; ++ph) {
-            if (live) ggp_coop_run_phase(ph, role, S, PRED ? ggp_ou(p, false) : ou_lik, 0.0, &T, false,
+            if (live) ggp_coop_run_phase(ph, role, S, SEGS ? ggp_ou(p, false) : ou_lik, 0.0, &T, false,
                                          PRED ? (seg_staged ? s_gl3[seg_from] : GGP_NO_GL3) : gl3_lik);
             GGP_CLK_MARK(1 + 2 * ph)
             ggp_coop_sync<GS>(group);
@@ -260,7 +263,7 @@ __global__ void __launch_bounds__(GGP_COOP_BLOCK(NG), NG == 1 ? 3 : (NG <= 4 ? 4
 // division and multiplied, :201-275); the time-reversed steps then run through the same four phases as the forward
 // passes with the sign-flipped parameters (mean_cov_model_r, :191-198).
 // ------------------------------------------------------------------------------------------------
-template <int NG, bool GS>
+template <int NG, bool GS, bool UNI = false>
 __global__ void __launch_bounds__(GGP_COOP_BLOCK(NG), NG == 1 ? 3 : (NG <= 4 ? 4 / NG : 1)) ggp_backward_coop_kernel(const GgpDevForest F, const GgpBwdArgs A) {
     GgpMathTables& T = *reinterpret_cast<GgpMathTables*>(ggp_smem);
     __shared__ int s_steps[NG * GGP_COOP_ROLES];
@@ -290,7 +293,7 @@ __global__ void __launch_bounds__(GGP_COOP_BLOCK(NG), NG == 1 ? 3 : (NG <= 4 ? 4
         t = leaf ? n - 1 : n;                       // mothers start at a virtual point: the daughters' first time
         from = leaf ? off + t : F.s_off[da];
         if (role == 0) {
-            const double* p0 = A.params + GGP_NP * F.seg[off + n - 1];
+            const double* p0 = UNI ? A.params : A.params + GGP_NP * F.seg[off + n - 1];
             double mu[4], C[16], R[16], rm[4];
             GgpState s;
             if (leaf) {
@@ -349,14 +352,15 @@ __global__ void __launch_bounds__(GGP_COOP_BLOCK(NG), NG == 1 ? 3 : (NG <= 4 ? 4
         S[GGP_CS_IN + 2] = F.x[at];
         S[GGP_CS_IN + 3] = F.g[at];
     }
-    int seg_at = steps > 0 ? F.seg[off + t - 1] : 0;
+    int seg_at = (!UNI && steps > 0) ? F.seg[off + t - 1] : 0;
+    const GgpOuParams ou_uni = ggp_ou(sp, true);   // UNI: one (sign-flipped) parameter set for the whole block
     ggp_coop_sync<GS>(group);
     for (int it = 0; it < max_steps; ++it) {
         const bool live = it < steps;
         const int in = GGP_CS_IN + 4 * (it & 1);
         if (GS && NG > 1 && (GGP_OPT_ALIGN_PERIOD == 1 || it % GGP_OPT_ALIGN_PERIOD == 0)) __syncthreads();
         const int64_t at = off + t - 1;   // the point this step arrives at
-        const int seg_next = it + 1 < steps ? F.seg[at - 1] : 0;
+        const int seg_next = (!UNI && it + 1 < steps) ? F.seg[at - 1] : 0;
         if (role == 0 && it + 1 < steps) {
             const int nx = GGP_CS_IN + 4 * ((it + 1) & 1);
             ggp_cp_async8(&S[nx + 0], F.time + at);
@@ -366,14 +370,14 @@ __global__ void __launch_bounds__(GGP_COOP_BLOCK(NG), NG == 1 ? 3 : (NG <= 4 ? 4
         }
         const double* pp = A.params;
         if (live) {
-            pp = seg_params(seg_at);
+            pp = UNI ? sp : seg_params(seg_at);
             const double dt = S[in + 0] - S[in + 1];
-            ggp_coop_run_phase(0, role, S, ggp_ou(pp, true), dt, &T);
+            ggp_coop_run_phase(0, role, S, UNI ? ou_uni : ggp_ou(pp, true), dt, &T);
         }
         ggp_coop_sync<GS>(group);
 #pragma unroll
         for (int ph = 1; ph < GGP_COOP_PHASES; ++ph) {
-            if (live) ggp_coop_run_phase(ph, role, S, ggp_ou(pp, true), 0.0, &T);
+            if (live) ggp_coop_run_phase(ph, role, S, UNI ? ou_uni : ggp_ou(pp, true), 0.0, &T);
             ggp_coop_sync<GS>(group);
         }
         if (live) {

@@ -158,6 +158,7 @@ cudaError_t opt_in_smem() {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(ggp_loglik_coop_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GGP_COOP_SMEM_BYTES(4));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(ggp_loglik_coop_kernel<4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GGP_COOP_SMEM_BYTES(4));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(ggp_loglik_coop_kernel<5, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GGP_COOP_SMEM_BYTES(5));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ggp_loglik_coop_kernel<3, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GGP_COOP_SMEM_BYTES(3));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(ggp_loglik_coop_kernel<1, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GGP_COOP_SMEM_BYTES(1));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(ggp_loglik_coop_kernel<GGP_PRED_NG, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GGP_COOP_SMEM_BYTES(GGP_PRED_NG));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(ggp_loglik_coop_kernel<GGP_PRED_UNI_NG, true, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GGP_COOP_SMEM_BYTES(GGP_PRED_UNI_NG));
@@ -448,6 +449,8 @@ int enqueue_loglik(ggp_forest* f, const double* d_params, int32_t n_vec, double*
                         ggp_loglik_coop_kernel<2, false><<<dim3((ng + 1) / 2, vc), GGP_COOP_BLOCK(2), GGP_COOP_SMEM_BYTES(2), ks>>>(F, A);
                     else if (f->coop_variant == 5)
                         ggp_loglik_coop_kernel<5, true, true><<<dim3((ng + 4) / 5, vc), GGP_COOP_BLOCK(5), GGP_COOP_SMEM_BYTES(5), ks>>>(F, A);
+                    else if (f->coop_variant == 6)   // 3 groups per block (occupancy experiment)
+                        ggp_loglik_coop_kernel<3, true, true><<<dim3((ng + 2) / 3, vc), GGP_COOP_BLOCK(3), GGP_COOP_SMEM_BYTES(3), ks>>>(F, A);
                     else if (f->coop_variant == 4)
                         ggp_loglik_coop_kernel<4, true, true><<<dim3((ng + 3) / 4, vc), GGP_COOP_BLOCK(4), GGP_COOP_SMEM_BYTES(4), ks>>>(F, A);
                     else if (f->coop_variant == 3)

@@ -17,7 +17,18 @@
 //           over twice the 32 kB L1.5 instruction cache, so every step streams from L2)
 #define GGP_COOP_BLOCK(NG) ((NG) * GGP_COOP_ROLES * 32)
 #define GGP_COOP_SEG_SMEM 8   // parameter sets (segments) staged in shared memory by the prediction passes
-#define GGP_COOP_SMEM_BYTES(NG) (sizeof(GgpMathTables) + (size_t)(NG) * GGP_CS_COUNT * GGP_COOP_CELLS * sizeof(double))
+// dynamic shared memory of the cooperative kernels: [math tables][replicated exp table, ggp_libm.cuh][scratch columns]
+#define GGP_COOP_SCRATCH_OFF (sizeof(GgpMathTables) + GGP_EXP_REP_BYTES)
+#define GGP_COOP_SMEM_BYTES(NG) (GGP_COOP_SCRATCH_OFF + (size_t)(NG) * GGP_CS_COUNT * GGP_COOP_CELLS * sizeof(double))
+// the math tables, then the eight-fold replica of exp's table (entry i of copy c at word 2 * (8 i + c)); ends with a block barrier
+__device__ __forceinline__ void ggp_coop_stage_tables(GgpMathTables* sm) {
+    ggp_stage_tables(sm);
+#if GGP_OPT_EXP_REP
+    uint64_t* rep = reinterpret_cast<uint64_t*>(ggp_smem + sizeof(GgpMathTables));
+    for (int i = threadIdx.x; i < 128 * 8 * 2; i += blockDim.x) rep[i] = sm->exp_tab[2 * (i >> 4) + (i & 1)];
+    __syncthreads();
+#endif
+}
 
 // barrier of one 4-warp group (GS: named barrier 1 + group, the groups of a block drift freely) or of the whole block
 template <bool GS>
@@ -88,9 +99,9 @@ __global__ void __launch_bounds__(GGP_COOP_BLOCK(NG), NG == 1 ? 3 : (NG <= 4 ? 4
     // parameters of segment s: from shared memory when staged (a per-step pointer chase through global memory otherwise)
     const bool seg_staged = A.n_seg <= GGP_COOP_SEG_SMEM;
     auto seg_params = [&](int s) -> const double* { return seg_staged ? sp + GGP_NP * s : A.params + GGP_NP * s; };
-    ggp_stage_tables(&T);   // ends with a block barrier
+    ggp_coop_stage_tables(&T);   // ends with a block barrier
     GgpScratch S;
-    S.base = reinterpret_cast<double*>(ggp_smem + sizeof(GgpMathTables)) + (size_t)group * GGP_CS_COUNT * GGP_COOP_CELLS + lane;
+    S.base = reinterpret_cast<double*>(ggp_smem + GGP_COOP_SCRATCH_OFF) + (size_t)group * GGP_CS_COUNT * GGP_COOP_CELLS + lane;
     S.stride = GGP_COOP_CELLS;
 
     const int gidx = blockIdx.x * NG + group;                  // 32-cell group inside this generation
@@ -273,9 +284,9 @@ __global__ void __launch_bounds__(GGP_COOP_BLOCK(NG), NG == 1 ? 3 : (NG <= 4 ? 4
     if ((int)threadIdx.x < GGP_NP * min(A.n_seg, GGP_COOP_SEG_SMEM)) sp[threadIdx.x] = A.params[threadIdx.x];
     const bool seg_staged = A.n_seg <= GGP_COOP_SEG_SMEM;
     auto seg_params = [&](int s) -> const double* { return seg_staged ? sp + GGP_NP * s : A.params + GGP_NP * s; };
-    ggp_stage_tables(&T);
+    ggp_coop_stage_tables(&T);
     GgpScratch S;
-    S.base = reinterpret_cast<double*>(ggp_smem + sizeof(GgpMathTables)) + (size_t)group * GGP_CS_COUNT * GGP_COOP_CELLS + lane;
+    S.base = reinterpret_cast<double*>(ggp_smem + GGP_COOP_SCRATCH_OFF) + (size_t)group * GGP_CS_COUNT * GGP_COOP_CELLS + lane;
     S.stride = GGP_COOP_CELLS;
 
     const int gidx = blockIdx.x * NG + group;
@@ -399,15 +410,15 @@ __global__ void __launch_bounds__(GGP_COOP_BLOCK(NG), NG == 1 ? 3 : (NG <= 4 ? 4
 // the roots' generation for ALL vectors of the chunk one after the other (32 roots per block, four roles), the other
 // generations use ggp_loglik_coop_kernel with one block column per vector.  A.carry [n_roots][16] in/out.
 // ------------------------------------------------------------------------------------------------
-#define GGP_COOP_SMEM_BYTES_CHAIN (sizeof(GgpMathTables) + (size_t)GGP_CS_COUNT_CHAIN * GGP_COOP_CELLS * sizeof(double))
+#define GGP_COOP_SMEM_BYTES_CHAIN (GGP_COOP_SCRATCH_OFF + (size_t)GGP_CS_COUNT_CHAIN * GGP_COOP_CELLS * sizeof(double))
 
 __global__ void __launch_bounds__(GGP_COOP_BLOCK(1), 3) ggp_loglik_chain_coop_kernel(const GgpDevForest F, const GgpFwdArgs A) {
     GgpMathTables& T = *reinterpret_cast<GgpMathTables*>(ggp_smem);
     __shared__ double sp[GGP_NP];
     const int role = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    ggp_stage_tables(&T);
+    ggp_coop_stage_tables(&T);
     GgpScratch S;
-    S.base = reinterpret_cast<double*>(ggp_smem + sizeof(GgpMathTables)) + lane;
+    S.base = reinterpret_cast<double*>(ggp_smem + GGP_COOP_SCRATCH_OFF) + lane;
     S.stride = GGP_COOP_CELLS;
     const int in_gen = blockIdx.x * GGP_COOP_CELLS + lane;
     const bool active = in_gen < A.n_slots;

@@ -250,12 +250,15 @@ def test_joints_segments_ragged():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("chunks", [1, 3, 7])
+@pytest.mark.parametrize("chunks", [1, 3, 7, "1,5,2,2"])
 def test_streamed_upload_evaluates_chunk_by_chunk(chunks, monkeypatch):
     """ggp_forest_upload_series cuts the series into chunks; the next evaluation runs a chunk's trees as soon as the chunk
     has landed.  Same per-cell sums as a forest created from the new series directly, whatever the chunking; also with
     parents stored after daughters and one-point cells (ragged forest)."""
-    monkeypatch.setenv("GGP_B200_UPLOAD_CHUNKS", str(chunks))
+    if isinstance(chunks, str):   # chunks of unequal size (relative sizes), each on its own stream like the equal ones
+        monkeypatch.setenv("GGP_B200_CHUNK_FRACTIONS", chunks)
+    else:
+        monkeypatch.setenv("GGP_B200_UPLOAD_CHUNKS", str(chunks))
     for d, P in ((ggp.simulate_forest(40, 4, seed=31), ggp.PARAMS_CONST_GAUSS), (ragged_forest(), ggp.PARAMS_SCALED_BINOMIAL)):
         f = ggp.Forest(d)
         ll0, pc0 = ggp.total_likelihood(P, f, per_cell=True)

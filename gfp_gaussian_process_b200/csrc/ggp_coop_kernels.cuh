@@ -203,13 +203,6 @@ __global__ void __launch_bounds__(GGP_COOP_BLOCK(NG), NG == 1 ? 3 : (NG <= 4 ? 4
             ggp_cp_async8(&S[nx + 2], F.x + at);
             ggp_cp_async8(&S[nx + 3], F.g + at);
         }
-        // LIK: the previous step's log-evidence term, left pending by phase 3 (ggp_coop.cuh), finished here where role 0 has slack
-        if (!PRED && role == 0 && pend) {
-            const double ll = ggp_coop_ll_deferred(GGP_SLOTS_REF(S), &T);
-            own = own + ll;
-            if (ll != ll) GGP_NAN_MIN(A.nan_key + A.v0 + v, F.s_dfs0[slot] + t);
-            pend = false;
-        }
         const double* pt = p;   // parameters of the point the step arrives at
         if (SEGS && live) {
             p = seg_params(seg_from);
@@ -219,7 +212,15 @@ __global__ void __launch_bounds__(GGP_COOP_BLOCK(NG), NG == 1 ? 3 : (NG <= 4 ? 4
             const double dt = S[in + 0] - S[in + 1];
             // same dt (and parameters) as this cell's previous step: GGP_CS_GE still holds the elementary exponentials
             const bool ge_same = role == 0 && it > 0 && dt == S[GGP_CS_K + GGP_K_T] && (!SEGS || seg_from == prev_seg);
-            ggp_coop_run_phase(0, role, S, SEGS ? ggp_ou(p, false) : ou_lik, dt, &T, ge_same);
+            // LIK: the previous step's log-evidence term, left pending by phase 3, is finished inside role 0's phase 0 (ggp_coop.cuh)
+            const bool take_ll = !PRED && role == 0 && pend;
+            double ll = 0.0;
+            ggp_coop_run_phase(0, role, S, SEGS ? ggp_ou(p, false) : ou_lik, dt, &T, ge_same, GGP_NO_GL3, take_ll ? &ll : nullptr);
+            if (take_ll) {
+                own = own + ll;
+                if (ll != ll) GGP_NAN_MIN(A.nan_key + A.v0 + v, F.s_dfs0[slot] + t);
+                pend = false;
+            }
             prev_seg = seg_from;
         }
         GGP_CLK_MARK(1)

@@ -131,9 +131,18 @@ int hc_loglik_coop(const ggp_forest_desc* d, const double* params, int n_vec, do
             };
             while (t + 1 < n) {
                 const double dt = F.time[off + t + 1] - F.time[from];
-                if (pend) finish_pending();
                 for (int ph = 0; ph < GGP_COOP_PHASES; ++ph)
-                    for (int role = 0; role < GGP_COOP_ROLES; ++role) ggp_coop_run_phase(ph, role, S, ggp_ou(p, false), dt, &g_tables);
+                    for (int role = 0; role < GGP_COOP_ROLES; ++role) {
+                        if (ph == 0 && role == 0 && pend) {   // as in the kernel: the pending term is finished inside role 0's phase 0
+                            double ll = 0.0;
+                            ggp_coop_run_phase(0, 0, S, ggp_ou(p, false), dt, &g_tables, false, GGP_NO_GL3, &ll);
+                            own = own + ll;
+                            if (ll != ll) GGP_NAN_MIN(&nan, F.s_dfs0[slot] + t);
+                            pend = false;
+                        } else {
+                            ggp_coop_run_phase(ph, role, S, ggp_ou(p, false), dt, &g_tables);
+                        }
+                    }
                 const int64_t at = off + t + 1;
                 for (int role = 0; role < GGP_COOP_ROLES; ++role) ggp_coop_ph3<true>(role, S, t < 0, p, F.x[at], F.g[at], F.model, &g_tables);
                 ++t;

@@ -51,6 +51,9 @@ __device__ __forceinline__ void ggp_cp_async_wait() { asm volatile("cp.async.wai
 #ifndef GGP_OPT_ALIGN_PERIOD
 #define GGP_OPT_ALIGN_PERIOD 4
 #endif
+#ifndef GGP_OPT_ROTATE_ROLES
+#define GGP_OPT_ROTATE_ROLES 0
+#endif
 #ifndef GGP_OPT_MERGE_BAR
 #define GGP_OPT_MERGE_BAR 1
 #endif
@@ -91,7 +94,9 @@ __global__ void __launch_bounds__(GGP_COOP_BLOCK(NG), NG == 1 ? 3 : (NG <= 4 ? 4
     __shared__ double sp[GGP_NP * (PRED ? GGP_COOP_SEG_SMEM : 1)];   // LIK: the vector's parameters; PRED: the first parameter sets
     __shared__ int s_steps[NG * GGP_COOP_ROLES];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int role = warp & (GGP_COOP_ROLES - 1), group = warp / GGP_COOP_ROLES;
+    // GGP_OPT_ROTATE_ROLES: group g's role r runs on scheduler (r + g) % 4, so that every scheduler hosts one warp of
+    // every role (the roles' FP64 loads differ per phase: cov_gg's scheduler needs 1.8x the pipe time of the others in phase 2)
+    const int group = warp / GGP_COOP_ROLES, role = (GGP_OPT_ROTATE_ROLES ? warp - group : warp) & (GGP_COOP_ROLES - 1);
     const int v = PRED ? 0 : blockIdx.y;
     if (!PRED && threadIdx.x < GGP_NP)
         sp[threadIdx.x] = A.params ? A.params[(int64_t)(A.v0 + v) * GGP_NP + threadIdx.x] : A.inline_params[(A.v0 + v) * GGP_NP + threadIdx.x];
@@ -281,7 +286,9 @@ __global__ void __launch_bounds__(GGP_COOP_BLOCK(NG), NG == 1 ? 3 : (NG <= 4 ? 4
     __shared__ int s_steps[NG * GGP_COOP_ROLES];
     __shared__ double sp[GGP_NP * GGP_COOP_SEG_SMEM];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int role = warp & (GGP_COOP_ROLES - 1), group = warp / GGP_COOP_ROLES;
+    // GGP_OPT_ROTATE_ROLES: group g's role r runs on scheduler (r + g) % 4, so that every scheduler hosts one warp of
+    // every role (the roles' FP64 loads differ per phase: cov_gg's scheduler needs 1.8x the pipe time of the others in phase 2)
+    const int group = warp / GGP_COOP_ROLES, role = (GGP_OPT_ROTATE_ROLES ? warp - group : warp) & (GGP_COOP_ROLES - 1);
     if ((int)threadIdx.x < GGP_NP * min(A.n_seg, GGP_COOP_SEG_SMEM)) sp[threadIdx.x] = A.params[threadIdx.x];
     const bool seg_staged = A.n_seg <= GGP_COOP_SEG_SMEM;
     auto seg_params = [&](int s) -> const double* { return seg_staged ? sp + GGP_NP * s : A.params + GGP_NP * s; };

@@ -32,7 +32,7 @@ F_ALG = 3700.0        # algorithmic FP64 flop per cell-timepoint per directional
 B_ALG = 28.0          # algorithmic bytes per cell-timepoint: time, x, g (f64) + segment (i32)
 # dram__bytes_read.sum + dram__bytes_write.sum of the likelihood kernel per cell-timepoint, from the ncu --set full capture
 # of the largest generation's launch (profiles/r01_s5_loglik_coop_gen5.txt, 6 399 691 ctp)
-DRAM_BYTES_PER_CTP_NCU = (204.177408e6 + 5.475840e6) / 6399691.0
+DRAM_BYTES_PER_CTP_NCU = (204.285440e6 + 4.971776e6) / 6399691.0
 METRIC = "cell-timepoints/s, FP64 log-likelihood evaluation (loglik evals/s in config)"
 
 

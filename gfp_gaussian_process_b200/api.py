@@ -163,8 +163,19 @@ def backward_cell_state(forest: Forest):
 def math_eval(fn, x, y=None, device=0):
     """device self-test of the strict exp/log/pow/dawson (ggp_math_eval)."""
     lib = _lib.load()
-    code = {"exp": 0, "log": 1, "pow": 2, "dawson": 3, "div": 4}[fn]
+    code = {"exp": 0, "log": 1, "pow": 2, "dawson": 3, "div": 4, "powexp": 5, "ll_finish": 6}[fn]
     x = np.ascontiguousarray(x, dtype=np.float64)
+    if fn == "ll_finish":     # x [n][5]: quadratic form, S00, S01, S10, S11 -> out [n]
+        n = x.shape[0]
+        out = np.empty(n)
+        _lib.check(lib.ggp_math_eval(device, code, n, x.ctypes.data_as(_lib.c_double_p), None, out.ctypes.data_as(_lib.c_double_p)))
+        return out
+    if fn == "powexp":        # x [n] bases, y [n] exp arguments -> out [n][5]: pow(x, 1.5 + i % 3), exp(y), exp(y/2), exp(-y), exp(y+1)
+        y = np.ascontiguousarray(np.broadcast_to(y, x.shape), dtype=np.float64)
+        out = np.empty((x.size, 5))
+        _lib.check(lib.ggp_math_eval(device, code, x.size, x.ctypes.data_as(_lib.c_double_p), y.ctypes.data_as(_lib.c_double_p),
+                                     out.ctypes.data_as(_lib.c_double_p)))
+        return out
     out = np.empty_like(x)
     yp = None
     if y is not None:

@@ -166,6 +166,7 @@ cudaError_t opt_in_smem() {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(ggp_backward_coop_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GGP_COOP_SMEM_BYTES(1));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(ggp_backward_coop_kernel<GGP_PRED_NG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GGP_COOP_SMEM_BYTES(GGP_PRED_NG));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(ggp_loglik_chain_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GGP_COOP_SMEM_BYTES_CHAIN);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ggp_coop_math_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GGP_COOP_SMEM_BYTES(1));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(ggp_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GGP_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(ggp_joint_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GGP_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(ggp_propagate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GGP_SMEM_BYTES);
@@ -660,17 +661,23 @@ int ggp_backward_cell_state(ggp_forest* f, double* out_cell_state20) {
 }
 
 int ggp_math_eval(int32_t device, int32_t fn, int64_t n, const double* x, const double* y, double* out) {
-    if (!x || !out || n <= 0 || fn < 0 || fn > 4 || (fn >= 2 && fn != 3 && !y)) return fail(GGP_ERR_BAD_ARG, "bad argument");
+    if (!x || !out || n <= 0 || fn < 0 || fn > 6 || ((fn == 2 || fn == 4 || fn == 5) && !y)) return fail(GGP_ERR_BAD_ARG, "bad argument");
     GGP_CUDA(cudaSetDevice(device));
+    const int64_t nx = fn == 6 ? 5 * n : n, nout = fn == 5 ? 5 * n : n;   // fn 6 reads five doubles per case, fn 5 writes five
     DevBuf<double> dx, dy, dout;
-    GGP_CUDA(dx.ensure(n));
+    GGP_CUDA(dx.ensure(nx));
     GGP_CUDA(dy.ensure(n));
-    GGP_CUDA(dout.ensure(n));
-    GGP_CUDA(cudaMemcpy(dx.p, x, n * sizeof(double), cudaMemcpyHostToDevice));
+    GGP_CUDA(dout.ensure(nout));
+    GGP_CUDA(cudaMemcpy(dx.p, x, nx * sizeof(double), cudaMemcpyHostToDevice));
     if (y) GGP_CUDA(cudaMemcpy(dy.p, y, n * sizeof(double), cudaMemcpyHostToDevice));
-    ggp_math_kernel<<<grid_of(n), GGP_BLOCK, sizeof(GgpMathTables)>>>(fn, n, dx.p, dy.p, dout.p);
+    if (fn >= 5) {
+        GGP_CUDA(opt_in_smem());
+        ggp_coop_math_kernel<<<(unsigned)((n + GGP_COOP_CELLS - 1) / GGP_COOP_CELLS), GGP_COOP_CELLS, GGP_COOP_SMEM_BYTES(1)>>>(fn, n, dx.p, dy.p, dout.p);
+    } else {
+        ggp_math_kernel<<<grid_of(n), GGP_BLOCK, sizeof(GgpMathTables)>>>(fn, n, dx.p, dy.p, dout.p);
+    }
     cudaError_t e = cudaDeviceSynchronize();
-    if (e == cudaSuccess) e = cudaMemcpy(out, dout.p, n * sizeof(double), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(out, dout.p, nout * sizeof(double), cudaMemcpyDeviceToHost);
     dx.release(); dy.release(); dout.release();
     if (e != cudaSuccess) return fail(GGP_ERR_CUDA, cudaGetErrorString(e));
     return GGP_OK;

@@ -525,3 +525,33 @@ __global__ void __launch_bounds__(GGP_COOP_BLOCK(1), 3) ggp_loglik_chain_coop_ke
         for (int i = role; i < 16; i += GGP_COOP_ROLES) A.carry[16 * (int64_t)F.s_root[slot] + i] = S[GGP_CS_CARRY + 4 + i];
     }
 }
+
+// ---- self-test of the fast paths the cooperative step adds on top of the strict math (ggp_math_eval fn 5, 6) ----
+// one warp per block, lane = test case, a full scratch column per lane (the slot helpers assume the 32-cell stride)
+//   fn 5: x = pow base, y = exp argument -> out[5 i] = pow(x, 1.5 + i % 3), out[5 i + 1..4] = exp of y, y / 2, -y, y + 1
+//         through ggp_pow_exp_slots (main paths interleaved, anything else through the out-of-line routines)
+//   fn 6: x[5 i ..] = quadratic form, S00, S01, S10, S11 -> the log-evidence term as role 0's phase 0 finishes it
+//         (shared-reciprocal division and log's main path inline, ggp_coop_ll_deferred otherwise)
+__global__ void __launch_bounds__(GGP_COOP_CELLS) ggp_coop_math_kernel(int fn, int64_t n, const double* __restrict__ x,
+                                                                      const double* __restrict__ y, double* __restrict__ out) {
+    GgpMathTables& T = *reinterpret_cast<GgpMathTables*>(ggp_smem);
+    ggp_coop_stage_tables(&T);
+    GgpScratch S;
+    S.base = reinterpret_cast<double*>(ggp_smem + GGP_COOP_SCRATCH_OFF) + threadIdx.x;
+    S.stride = GGP_COOP_CELLS;
+    const int64_t i = (int64_t)blockIdx.x * GGP_COOP_CELLS + threadIdx.x;
+    if (i >= n) return;
+    if (fn == 5) {
+        S[GGP_CS_EC + 0] = y[i]; S[GGP_CS_EC + 1] = y[i] / 2; S[GGP_CS_EC + 2] = -y[i]; S[GGP_CS_EC + 3] = y[i] + 1;
+        out[5 * i] = ggp_pow_exp_slots(x[i], 1.5 + (double)(i % 3), GGP_SLOTS_REF(S), GGP_CS_EC, 4, &T);
+        for (int k = 0; k < 4; ++k) out[5 * i + 1 + k] = S[GGP_CS_EC + k];
+    } else {
+        for (int k = 0; k < 14; ++k) S[GGP_CS_ST + k] = k < 4 ? 1.0 : (k == 4 || k == 8 || k == 11 || k == 13 ? 1.0 : 0.125);
+        for (int k = 0; k < 5; ++k) S[GGP_CS_LL + k] = x[5 * i + k];
+        GgpOuParams p;
+        p.ml = 0.01; p.gl = 0.01; p.sl2 = 1e-5; p.mq = 10.; p.gq = 0.01; p.sq2 = 0.1; p.b = 1e-3;
+        double ll = 0.0;
+        ggp_coop_run_phase(0, 0, S, p, 1.0, &T, false, GGP_NO_GL3, &ll);
+        out[i] = ll;
+    }
+}

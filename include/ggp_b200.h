@@ -143,7 +143,11 @@ const char* ggp_version(void);
 
 /* device self-test of the strict math (exp/log/pow/Dawson/propagate) for callers that hold expected bits:
  * evaluates fn over n inputs on the device.  fn: 0 exp, 1 log, 2 pow(x, y), 3 dawson, 4 x / y through the shared-reciprocal
- * divisor path (GgpDivisor).  y may be NULL for 0, 1, 3. */
+ * divisor path (GgpDivisor).  y may be NULL for 0, 1, 3, 6.
+ * 5: the interleaved pow + exp block of the cooperative step: out[5 i] = pow(x[i], 1.5 + i % 3), out[5 i + 1..4] = exp of
+ *    y[i], y[i] / 2, -y[i], y[i] + 1 (out holds 5 n doubles).
+ * 6: the log-evidence term (likelihood.h:26-32) as the cooperative step finishes it inside a phase: x holds 5 n doubles
+ *    (quadratic form -1/2 r^T S^-1 r, S00, S01, S10, S11 per case), out[i] = the term. */
 int ggp_math_eval(int32_t device, int32_t fn, int64_t n, const double* x, const double* y, double* out);
 /* propagate n independent states (14 doubles each: 4 means + upper triangle) over dt[i] with 7 OU params each
  * (mean_cov_model, mean_cov_model.h:211); cross (NULL or [n][16]) receives cross_cov_model (:380). */

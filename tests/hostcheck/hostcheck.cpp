@@ -13,6 +13,10 @@ extern "C" {
 void hc_exp(long n, const double* x, double* y) { for (long i = 0; i < n; ++i) y[i] = ggp_exp(x[i], &g_tables); }
 void hc_log(long n, const double* x, double* y) { for (long i = 0; i < n; ++i) y[i] = ggp_log(x[i], &g_tables); }
 void hc_pow(long n, const double* x, const double* e, double* y) { for (long i = 0; i < n; ++i) y[i] = ggp_pow(x[i], e[i], &g_tables); }
+// the log-evidence term from the quadratic form on (ggp_filter.cuh::ggp_log_evidence_finish): in5 [n][5] = qf, S00, S01, S10, S11
+void hc_ll_finish(long n, const double* in5, double* y) {
+    for (long i = 0; i < n; ++i) y[i] = ggp_log_evidence_finish(in5[5 * i], in5[5 * i + 1], in5[5 * i + 2], in5[5 * i + 3], in5[5 * i + 4], &g_tables);
+}
 void hc_dawson(long n, const double* x, double* y) { for (long i = 0; i < n; ++i) y[i] = ggp_dawson(x[i], &g_tables); }
 // state = 4 means + 10 upper-triangular covariances (xx,xg,xl,xq,gg,gl,gq,ll,lq,qq)
 void hc_propagate(long n, const double* state14, const double* dt, const double* p7, double* out14) {

@@ -36,6 +36,40 @@ def test_device_math_bits(golden_dir):
     assert same_bits(api.math_eval("dawson", xs), np.array([L.ggp_oracle_dawson(v) for v in xs]))
 
 
+def test_fast_paths_of_the_cooperative_step_fall_back_exactly():
+    """The cooperative step evaluates pow with a role's exponentials as one interleaved block and finishes the
+    log-evidence term inline (shared-reciprocal division, log's main path); every argument outside those main paths
+    must go through the out-of-line routines and give the same bits: ordinary, tiny, huge, zero, negative, inf, nan."""
+    import ctypes as C
+    from hostpass import hc
+    rng = np.random.default_rng(11)
+    sp = np.array([0.0, -0.0, 1.0, -1.0, np.inf, -np.inf, np.nan, 5e-324, 1e-310, 2.2250738585072014e-308, 1.7e308,
+                   1e-20, 1e-17, 600.0, -600.0, 720.0, -745.2, 1100.0, -1100.0, 1 - 2.0 ** -53, 1 + 2.0 ** -52, 0.97, 1.03])
+    # pow + exp block
+    base = np.concatenate([10 ** rng.uniform(-12, 4, 20000), rng.uniform(0.9, 1.1, 2000), sp, rng.permutation(sp)])
+    arg = np.concatenate([rng.uniform(-40, 40, 20000), 10 ** rng.uniform(-25, 3, 2000) * rng.choice([-1, 1], 2000), rng.permutation(sp), sp])
+    got = api.math_eval("powexp", base, arg)
+    e = 1.5 + (np.arange(base.size) % 3)
+    with np.errstate(all="ignore"):
+        ref = np.stack([api.math_eval("pow", base, e), api.math_eval("exp", arg), api.math_eval("exp", arg / 2),
+                        api.math_eval("exp", -arg), api.math_eval("exp", arg + 1)], axis=1)
+    assert same_bits(got, ref)
+    # log-evidence term: random well-conditioned S, S with a row exchange, det near 1, singular / negative / non-finite S
+    n = 20000
+    S00 = 10 ** rng.uniform(-4, 6, n); S11 = 10 ** rng.uniform(-4, 6, n)
+    rho = rng.uniform(-0.99, 0.99, n)
+    S01 = rho * np.sqrt(S00 * S11); S10 = S01 * (1 + rng.choice([0, 2.0 ** -52, -2.0 ** -52], n))
+    qf = -rng.uniform(0, 50, n)
+    cases = np.stack([qf, S00, S01, S10, S11], axis=1)
+    near1 = np.stack([qf[:500], 1 + rng.uniform(-0.05, 0.05, 500), np.zeros(500), np.zeros(500), np.ones(500)], axis=1)
+    a3, b3 = [v.reshape(-1) for v in np.meshgrid(sp, sp)]
+    odd = np.stack([np.full(a3.size, -1.5), a3, b3, b3[::-1], a3[::-1]], axis=1)
+    cases = np.ascontiguousarray(np.concatenate([cases, near1, odd]))
+    ref = np.empty(cases.shape[0])
+    hc().hc_ll_finish(C.c_long(cases.shape[0]), cases.ctypes.data_as(C.POINTER(C.c_double)), ref.ctypes.data_as(C.POINTER(C.c_double)))
+    assert same_bits(api.math_eval("ll_finish", cases), ref)
+
+
 def test_shared_reciprocal_division_is_ieee():
     """a / GgpDivisor(b) must be the correctly rounded quotient (what the host's `/` returns) for every operand
     class: the step's ~190 divisions per time point go through it"""

@@ -125,3 +125,18 @@ def test_step_matches_live_reference(hc):
         mo, co = oracle_py.mean_cov_model(mf[i], cf[i], 15.0, PARAMS_SCALED_BINOMIAL[:7], which="ref")
         assert same_bits(out[k, :4], mo)
         assert same_bits(out[k, 4:], co.reshape(4, 4)[iu])
+
+
+def test_log_evidence_finish_matches_numpy_on_ordinary_input(hc):
+    """hc_ll_finish (the product's ggp_log_evidence_finish on the host, the reference of the device self-test fn 6)
+    against a direct numpy evaluation of likelihood.h:26-32 from the quadratic form on"""
+    rng = np.random.default_rng(2)
+    n = 2000
+    S00 = 10 ** rng.uniform(-3, 5, n); S11 = 10 ** rng.uniform(-3, 5, n)
+    S01 = rng.uniform(-0.9, 0.9, n) * np.sqrt(S00 * S11)
+    qf = -rng.uniform(0, 30, n)
+    cases = np.ascontiguousarray(np.stack([qf, S00, S01, S01, S11], axis=1))
+    out = np.empty(n)
+    hc.hc_ll_finish(C.c_long(n), _p(cases), _p(out))
+    ref = qf - 0.5 * np.log(S00 * S11 - S01 * S01) - 2 * np.log(2 * np.pi)
+    assert np.max(np.abs(out - ref) / np.abs(ref)) < 1e-12

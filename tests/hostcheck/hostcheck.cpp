@@ -86,6 +86,19 @@ int hc_loglik(const ggp_forest_desc* d, const double* params, int n_vec, double*
     return 0;
 }
 
+// upload chunks of the layout (ggp_layout.hpp): ctp_chunk_start [n_chunks+1], chunk of every cell [n_cells] (from the
+// per-generation slot ranges), returns the number of chunks or -1
+int hc_layout_chunks(const ggp_forest_desc* d, int want_chunks, const double* fractions, long long* ctp_chunk_start, int* chunk_of_cell) {
+    GgpLayout L;
+    if (!L.build(d, want_chunks, fractions).empty()) return -1;
+    for (int k = 0; k <= L.n_chunks; ++k) ctp_chunk_start[k] = L.ctp_chunk_start[k];
+    for (int g = 0; g < L.n_gen; ++g)
+        for (int k = 0; k < L.n_chunks; ++k) {
+            const int64_t* row = L.gen_chunk_start.data() + (size_t)g * (L.n_chunks + 1);
+            for (int64_t s = row[k]; s < row[k + 1]; ++s) chunk_of_cell[L.cell_of_slot[s]] = k;
+        }
+    return L.n_chunks;
+}
 // the likelihood with the cooperative step (ggp_coop.cuh): the four roles of every phase run in sequence over one
 // cell's scratch column, in the order of ggp_loglik_coop_kernel (ggp_coop_kernels.cuh).  fresh mode only.
 int hc_loglik_coop(const ggp_forest_desc* d, const double* params, int n_vec, double* out_cell_ll, long long* nan_rank) {

@@ -165,3 +165,36 @@ def test_io_readers(tmp_path):
     assert ids == ["1.1", "1.2", "1.3"] and data.parent.tolist() == [-1, 0, 0]
     assert data.daughter1.tolist() == [1, -1, -1] and data.daughter2.tolist() == [2, -1, -1]
     assert data.time.tolist() == [0, 1, 2, 2, 3] and data.log_length[0] == np.log(2.0)
+
+
+def test_upload_chunks_keep_trees_together_and_cover_the_series():
+    """ggp_layout.hpp: the series are cut into contiguous chunks (equal, or of given relative sizes); a tree belongs to the
+    chunk its LAST point arrives with, so every cell of a tree sits in one chunk and all its points have landed when that
+    chunk has; the chunk boundaries are monotone and cover [0, n_ctp)."""
+    import ctypes as C
+    from hostpass import hc, make_desc
+    data = ggp.simulate_forest(37, 4, seed=3)
+    desc = make_desc(data)
+    root = np.arange(data.n_cells)
+    for c in range(data.n_cells):          # parents precede daughters in the generator's order
+        if data.parent[c] >= 0:
+            root[c] = root[data.parent[c]]
+    last = data.cell_offset[1:] - 1
+    for want, fr in ((1, None), (3, None), (7, None), (4, [1.0, 5.0, 2.0, 2.0]), (3, [1e-9, 1.0, 1.0])):
+        starts = np.zeros(want + 1, dtype=np.int64)
+        chunk = np.full(data.n_cells, -1, dtype=np.int32)
+        frp = (C.c_double * want)(*fr) if fr else None
+        k = hc().hc_layout_chunks(C.byref(desc), want, frp, starts.ctypes.data_as(C.POINTER(C.c_longlong)),
+                                  chunk.ctypes.data_as(C.POINTER(C.c_int)))
+        assert k == want
+        assert starts[0] == 0 and starts[-1] == data.n_ctp and np.all(np.diff(starts) >= 0)
+        if fr:
+            w = np.cumsum([0.0] + fr) / sum(fr)
+            assert np.all(np.abs(starts - w * data.n_ctp) <= 1)
+        assert np.all(chunk >= 0)
+        for r in np.unique(root):
+            cells = np.nonzero(root == r)[0]
+            assert len(set(chunk[cells])) == 1                               # a tree is never split
+            k_tree = chunk[cells[0]]
+            assert last[cells].max() < starts[k_tree + 1]                    # all its points have landed with that chunk
+            assert last[cells].max() >= starts[k_tree]                       # and not earlier: it is the chunk of the last point

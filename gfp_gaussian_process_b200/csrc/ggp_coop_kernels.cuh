@@ -17,18 +17,10 @@
 //           over twice the 32 kB L1.5 instruction cache, so every step streams from L2)
 #define GGP_COOP_BLOCK(NG) ((NG) * GGP_COOP_ROLES * 32)
 #define GGP_COOP_SEG_SMEM 8   // parameter sets (segments) staged in shared memory by the prediction passes
-// dynamic shared memory of the cooperative kernels: [math tables][replicated exp table, ggp_libm.cuh][scratch columns]
-#define GGP_COOP_SCRATCH_OFF (sizeof(GgpMathTables) + GGP_EXP_REP_BYTES)
+// dynamic shared memory of the cooperative kernels: [math tables][scratch columns]
+#define GGP_COOP_SCRATCH_OFF (sizeof(GgpMathTables))
 #define GGP_COOP_SMEM_BYTES(NG) (GGP_COOP_SCRATCH_OFF + (size_t)(NG) * GGP_CS_COUNT * GGP_COOP_CELLS * sizeof(double))
-// the math tables, then the eight-fold replica of exp's table (entry i of copy c at word 2 * (8 i + c)); ends with a block barrier
-__device__ __forceinline__ void ggp_coop_stage_tables(GgpMathTables* sm) {
-    ggp_stage_tables(sm);
-#if GGP_OPT_EXP_REP
-    uint64_t* rep = reinterpret_cast<uint64_t*>(ggp_smem + sizeof(GgpMathTables));
-    for (int i = threadIdx.x; i < 128 * 8 * 2; i += blockDim.x) rep[i] = sm->exp_tab[2 * (i >> 4) + (i & 1)];
-    __syncthreads();
-#endif
-}
+__device__ __forceinline__ void ggp_coop_stage_tables(GgpMathTables* sm) { ggp_stage_tables(sm); }   // ends with a block barrier
 
 // barrier of one 4-warp group (GS: named barrier 1 + group, the groups of a block drift freely) or of the whole block
 template <bool GS>
@@ -45,14 +37,8 @@ __device__ __forceinline__ void ggp_cp_async_wait() { asm volatile("cp.async.wai
 
 // Profiling aid (never in the shipped build): -DGGP_PHASE_CLOCKS accumulates, per role, the SM clocks spent inside each
 // phase and waiting at each barrier of the likelihood step (ggp_debug_phase_clocks reads them; tools/phase_clocks.py).
-#ifndef GGP_OPT_STAGGER_NS
-#define GGP_OPT_STAGGER_NS 0
-#endif
 #ifndef GGP_OPT_ALIGN_PERIOD
 #define GGP_OPT_ALIGN_PERIOD 4
-#endif
-#ifndef GGP_OPT_ROTATE_ROLES
-#define GGP_OPT_ROTATE_ROLES 0
 #endif
 #ifndef GGP_OPT_MERGE_BAR
 #define GGP_OPT_MERGE_BAR 1
@@ -94,9 +80,7 @@ __global__ void __launch_bounds__(GGP_COOP_BLOCK(NG), NG == 1 ? 3 : (NG <= 4 ? 4
     __shared__ double sp[GGP_NP * (PRED ? GGP_COOP_SEG_SMEM : 1)];   // LIK: the vector's parameters; PRED: the first parameter sets
     __shared__ int s_steps[NG * GGP_COOP_ROLES];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // GGP_OPT_ROTATE_ROLES: group g's role r runs on scheduler (r + g) % 4, so that every scheduler hosts one warp of
-    // every role (the roles' FP64 loads differ per phase: cov_gg's scheduler needs 1.8x the pipe time of the others in phase 2)
-    const int group = warp / GGP_COOP_ROLES, role = (GGP_OPT_ROTATE_ROLES ? warp - group : warp) & (GGP_COOP_ROLES - 1);
+    const int group = warp / GGP_COOP_ROLES, role = warp & (GGP_COOP_ROLES - 1);
     const int v = PRED ? 0 : blockIdx.y;
     if (!PRED && threadIdx.x < GGP_NP)
         sp[threadIdx.x] = A.params ? A.params[(int64_t)(A.v0 + v) * GGP_NP + threadIdx.x] : A.inline_params[(A.v0 + v) * GGP_NP + threadIdx.x];
@@ -186,11 +170,6 @@ __global__ void __launch_bounds__(GGP_COOP_BLOCK(NG), NG == 1 ? 3 : (NG <= 4 ? 4
     int seg_from = (SEGS && active) ? F.seg[from] : 0;
     int seg_at = (SEGS && steps > 0) ? F.seg[off + t + 1] : 0;
     ggp_coop_sync<GS>(group);
-#if GGP_OPT_STAGGER_NS > 0
-    // free-running groups (no step alignment): the second half of the block's groups starts half a step late, so that the
-    // two halves sit in different phases (FP64-heavy slot loops vs shared-memory-heavy role code) from then on
-    if (!PRED && NG > 1 && GS && !STEP_ALIGN && group >= NG / 2) __nanosleep(GGP_OPT_STAGGER_NS);
-#endif
     bool pend = false;   // LIK, role 0: a log-evidence term is pending in GGP_CS_LL
     GGP_CLK_DECL
     for (int it = 0; it < max_steps; ++it) {
@@ -286,9 +265,7 @@ __global__ void __launch_bounds__(GGP_COOP_BLOCK(NG), NG == 1 ? 3 : (NG <= 4 ? 4
     __shared__ int s_steps[NG * GGP_COOP_ROLES];
     __shared__ double sp[GGP_NP * GGP_COOP_SEG_SMEM];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // GGP_OPT_ROTATE_ROLES: group g's role r runs on scheduler (r + g) % 4, so that every scheduler hosts one warp of
-    // every role (the roles' FP64 loads differ per phase: cov_gg's scheduler needs 1.8x the pipe time of the others in phase 2)
-    const int group = warp / GGP_COOP_ROLES, role = (GGP_OPT_ROTATE_ROLES ? warp - group : warp) & (GGP_COOP_ROLES - 1);
+    const int group = warp / GGP_COOP_ROLES, role = warp & (GGP_COOP_ROLES - 1);
     if ((int)threadIdx.x < GGP_NP * min(A.n_seg, GGP_COOP_SEG_SMEM)) sp[threadIdx.x] = A.params[threadIdx.x];
     const bool seg_staged = A.n_seg <= GGP_COOP_SEG_SMEM;
     auto seg_params = [&](int s) -> const double* { return seg_staged ? sp + GGP_NP * s : A.params + GGP_NP * s; };

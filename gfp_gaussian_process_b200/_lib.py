@@ -48,7 +48,7 @@ SIGNATURES = {
     "ggp_forest_create": (C.c_int, [C.POINTER(ForestDesc), C.POINTER(C.c_void_p)]),
     "ggp_forest_destroy": (None, [C.c_void_p]),
     "ggp_forest_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
-    "ggp_forest_upload_series": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ggp_forest_upload_series": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ggp_forest_n_cells": (C.c_int64, [C.c_void_p]),
     "ggp_forest_n_ctp": (C.c_int64, [C.c_void_p]),
     "ggp_forest_n_roots": (C.c_int64, [C.c_void_p]),

@@ -152,6 +152,16 @@ def collect_joint_distributions(forest: Forest, params_vecs, tolerance_joint=1e-
     return row[:n], col[:n], rec[:n, :8], rec[:n, 8:]
 
 
+def count_joints(forest: Forest, params_vecs, tolerance_joint=1e-10, row_begin=0, row_end=None):
+    """number of joints the start points row_begin <= ctp < row_end emit (the walk without storing records)"""
+    lib = _lib.load()
+    p, _ = _as_params(params_vecs)
+    cnt = C.c_int64(0)
+    _lib.check(lib.ggp_joints(forest.handle, p.ctypes.data_as(_lib.c_double_p), p.shape[0], C.c_double(tolerance_joint), row_begin,
+                              forest.n_ctp if row_end is None else row_end, 0, C.byref(cnt), None, None, None))
+    return cnt.value
+
+
 def backward_cell_state(forest: Forest):
     """each cell's MOMAdata::mean/cov as the backward pass leaves them (sign-flipped frame)."""
     lib = _lib.load()

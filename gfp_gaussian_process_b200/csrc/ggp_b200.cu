@@ -54,6 +54,10 @@ template <class T>
 struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }   // scratch buffers of a call are freed on every return path
     cudaError_t ensure(size_t count) {
         if (count <= n) return cudaSuccess;
         if (p) cudaFree(p);
@@ -73,6 +77,15 @@ struct DevBuf {
         p = nullptr;
         n = 0;
     }
+};
+
+struct ScopedEvent {
+    cudaEvent_t ev = nullptr;
+    ScopedEvent() = default;
+    ScopedEvent(const ScopedEvent&) = delete;
+    ScopedEvent& operator=(const ScopedEvent&) = delete;
+    ~ScopedEvent() { if (ev) cudaEventDestroy(ev); }
+    cudaError_t create() { return cudaEventCreate(&ev); }
 };
 
 }  // namespace
@@ -101,8 +114,11 @@ struct ggp_forest {
     cudaEvent_t tl_upload0 = nullptr;
     std::vector<cudaEvent_t> tl_begin, tl_end;
     bool upload_pending = false;
+    bool compute_init = false;            // created with compute_init = 1: upload_series re-derives the init_cells statistics
+    std::vector<double> edge;             // [4][n_cells] first x, last x, first g, last g of every cell (host copy for that re-derivation)
+    std::vector<int64_t> h_off;           // [n_cells+1] caller's cell offsets (kept with `edge`)
     const double* h_inline_params = nullptr;   // set by ggp_loglik for the duration of one streamed evaluation
-    int64_t coop_ng4_min_groups = 4 * 148 * 2;   // launches with at least this many 32-cell groups use 4 groups per block
+    int64_t coop_ng4_min_groups = 0;      // launches with at least this many 32-cell groups use 4 groups per block (8 per SM; set at create)
     int coop_variant = 4;                 // GGP_B200_COOP_VARIANT (A/B measurements): 0 = 4 groups/block, block barriers; 2 = 2 groups/block; 3 = 4 groups, per-group barriers
     bool legacy_loglik = false;           // GGP_B200_LEGACY_LOGLIK=1: one-thread-per-cell likelihood kernel (A/B measurements)
     // device
@@ -121,9 +137,11 @@ struct ggp_forest {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double last_ms = 0.0;
     int64_t last_launches = 0;
-    int64_t state_budget_bytes = (int64_t)8 << 30;
-    int n_sm = 148;
+    int64_t state_budget_bytes = (int64_t)8 << 30;   // end-of-cell state of one vector chunk (n_vec * n_cells * 112 B); GGP_B200_STATE_BUDGET overrides (bytes)
+    int n_sm = 0;                 // cudaDevAttrMultiProcessorCount of the handle's device
     int walk_blocks_per_sm = 1;   // joints walker blocks (256 threads) resident per SM (register-limited); GGP_B200_WALK_BLOCKS overrides
+    int64_t walk_total_blocks = 0;   // GGP_B200_WALK_TOTAL_BLOCKS: cap on the number of walker blocks (tests: results do not depend on it)
+    unsigned fill_grid(size_t cnt) const { return (unsigned)std::max<size_t>(1, std::min<size_t>((cnt + 255) / 256, (size_t)n_sm * 8)); }
 
     GgpDevForest dev() const {
         GgpDevForest F;
@@ -224,6 +242,18 @@ int ggp_forest_create(const ggp_forest_desc* d, ggp_forest** out) {
     f->model.noise_scaled = d->noise_model == GGP_NOISE_SCALED;
     f->model.division_binomial = d->division_model == GGP_DIVISION_BINOMIAL;
     f->model.fp_auto = d->fp_auto;
+    f->compute_init = d->compute_init != 0;
+    if (f->compute_init) {
+        f->edge.resize((size_t)4 * L.n_cells);
+        f->h_off.assign(d->cell_offset, d->cell_offset + L.n_cells + 1);
+        for (int64_t c = 0; c < L.n_cells; ++c) {
+            const int64_t o = d->cell_offset[c], l = d->cell_offset[c + 1] - 1;
+            f->edge[c] = d->log_length[o];
+            f->edge[L.n_cells + c] = d->log_length[l];
+            f->edge[2 * L.n_cells + c] = d->fp[o];
+            f->edge[3 * L.n_cells + c] = d->fp[l];
+        }
+    }
     {
         const int K = L.n_chunks;
         f->gen_partial0.assign((size_t)L.n_gen * (K + 1), 0);
@@ -238,11 +268,15 @@ int ggp_forest_create(const ggp_forest_desc* d, ggp_forest** out) {
     {
         const char* lg = getenv("GGP_B200_LEGACY_LOGLIK");
         f->legacy_loglik = lg && lg[0] == '1';
+        int n_sm = 0;
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, f->device);
+        f->n_sm = std::max(n_sm, 1);
+        f->coop_ng4_min_groups = (int64_t)4 * f->n_sm * 2;
         if (const char* m = getenv("GGP_B200_NG4_MIN")) f->coop_ng4_min_groups = atoll(m);
         if (const char* m = getenv("GGP_B200_COOP_VARIANT")) f->coop_variant = atoi(m);
         if (const char* m = getenv("GGP_B200_WALK_BLOCKS")) f->walk_blocks_per_sm = std::max(1, atoi(m));
-        int n_sm = 0;
-        if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, f->device) == cudaSuccess && n_sm > 0) f->n_sm = n_sm;
+        if (const char* m = getenv("GGP_B200_WALK_TOTAL_BLOCKS")) f->walk_total_blocks = std::max<int64_t>(0, atoll(m));
+        if (const char* m = getenv("GGP_B200_STATE_BUDGET")) f->state_budget_bytes = std::max<int64_t>(1, atoll(m));
     }
 
     cudaStream_t s = nullptr;
@@ -315,6 +349,9 @@ void ggp_forest_destroy(ggp_forest* f) {
     if (f->compute_done) cudaEventDestroy(f->compute_done);
     if (f->eval_start) cudaEventDestroy(f->eval_start);
     for (cudaEvent_t ev : f->chunk_done) if (ev) cudaEventDestroy(ev);
+    if (f->tl_upload0) cudaEventDestroy(f->tl_upload0);
+    for (cudaEvent_t ev : f->tl_begin) if (ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : f->tl_end) if (ev) cudaEventDestroy(ev);
     for (cudaStream_t st : f->chunk_stream) if (st) cudaStreamDestroy(st);
     if (f->copy_stream) cudaStreamDestroy(f->copy_stream);
     if (f->ev0) cudaEventDestroy(f->ev0);
@@ -328,9 +365,40 @@ int ggp_forest_set_stream(ggp_forest* f, void* cuda_stream) {
     return GGP_OK;
 }
 
-int ggp_forest_upload_series(ggp_forest* f, const double* time, const double* log_length, const double* fp) {
+int ggp_forest_upload_series(ggp_forest* f, const double* time, const double* log_length, const double* fp,
+                             const double* init_f4, const double* init_r4) {
     if (int rc = check_handle(f)) return rc;
-    if (!time || !log_length || !fp) return fail(GGP_ERR_BAD_ARG, "null series");
+    if (!time && !log_length && !fp) return fail(GGP_ERR_BAD_ARG, "no series given");
+    if ((init_f4 == nullptr) != (init_r4 == nullptr)) return fail(GGP_ERR_BAD_ARG, "init_f4 and init_r4 go together");
+    // the root / leaf priors are statistics of the CURRENT measurements (init_cells_f/r, moma_input.h:675-735)
+    if (init_f4) {
+        for (int i = 0; i < 4; ++i) { f->L.init_f[i] = init_f4[i]; f->L.init_r[i] = init_r4[i]; }
+    } else if (log_length || fp) {
+        if (!f->compute_init)
+            return fail(GGP_ERR_BAD_ARG, "new measurements need their init_cells statistics: this forest was created with statistics of a "
+                                         "larger data set (compute_init = 0), pass init_f4 / init_r4 (ggp_init_stats)");
+        const int64_t N = f->n_cells;
+        const std::vector<int64_t>& off = f->h_off;
+        for (int64_t c = 0; c < N; ++c) {
+            const int64_t o = off[c], l = off[c + 1] - 1;
+            if (log_length) { f->edge[c] = log_length[o]; f->edge[N + c] = log_length[l]; }
+            if (fp) { f->edge[2 * N + c] = fp[o]; f->edge[3 * N + c] = fp[l]; }
+        }
+        for (int dir = 0; dir < 2; ++dir) {   // GgpLayout::init_stats on the edge values: same sums in the same order
+            double sx = 0, sg = 0, sxx = 0, sgg = 0;
+            int64_t cnt = 0;
+            const double* ex = f->edge.data() + (size_t)dir * N;
+            const double* eg = f->edge.data() + (size_t)(2 + dir) * N;
+            for (int64_t c = 0; c < N; ++c)
+                if (off[c + 1] - off[c] > 1) {
+                    sx += ex[c]; sg += eg[c]; sxx += ex[c] * ex[c]; sgg += eg[c] * eg[c];
+                    ++cnt;
+                }
+            double* out = dir == 0 ? f->L.init_f : f->L.init_r;
+            const double mx = sx / cnt, mg = sg / cnt;
+            out[0] = mx; out[1] = mg; out[2] = sxx / cnt - mx * mx; out[3] = sgg / cnt - mg * mg;
+        }
+    }
     GGP_CUDA(cudaSetDevice(f->device));
     // the copies run on their own stream, chunk by chunk, behind whatever the handle's stream still reads; the next
     // likelihood evaluation starts on a chunk's trees as soon as that chunk has landed (enqueue_loglik)
@@ -340,9 +408,9 @@ int ggp_forest_upload_series(ggp_forest* f, const double* time, const double* lo
     for (int k = 0; k < f->L.n_chunks; ++k) {
         const int64_t c0 = f->L.ctp_chunk_start[k];
         const size_t b = (size_t)(f->L.ctp_chunk_start[k + 1] - c0) * sizeof(double);
-        GGP_CUDA(cudaMemcpyAsync(f->time.p + c0, time + c0, b, cudaMemcpyHostToDevice, f->copy_stream));
-        GGP_CUDA(cudaMemcpyAsync(f->x.p + c0, log_length + c0, b, cudaMemcpyHostToDevice, f->copy_stream));
-        GGP_CUDA(cudaMemcpyAsync(f->g.p + c0, fp + c0, b, cudaMemcpyHostToDevice, f->copy_stream));
+        if (time) GGP_CUDA(cudaMemcpyAsync(f->time.p + c0, time + c0, b, cudaMemcpyHostToDevice, f->copy_stream));
+        if (log_length) GGP_CUDA(cudaMemcpyAsync(f->x.p + c0, log_length + c0, b, cudaMemcpyHostToDevice, f->copy_stream));
+        if (fp) GGP_CUDA(cudaMemcpyAsync(f->g.p + c0, fp + c0, b, cudaMemcpyHostToDevice, f->copy_stream));
         GGP_CUDA(cudaEventRecord(f->chunk_ready[k], f->copy_stream));
     }
     f->upload_pending = true;
@@ -408,7 +476,7 @@ int enqueue_loglik(ggp_forest* f, const double* d_params, int32_t n_vec, double*
         // launches do not write every partial (whole-generation launches pack their groups, 128-cell legacy blocks)
         {
             const size_t cnt = (size_t)vc * n_partial;
-            ggp_fill64_kernel<<<(unsigned)std::min<size_t>((cnt + 255) / 256, 1184), 256, 0, f->stream>>>(reinterpret_cast<unsigned long long*>(f->w_partial.p), 0ull, cnt);
+            ggp_fill64_kernel<<<f->fill_grid(cnt), 256, 0, f->stream>>>(reinterpret_cast<unsigned long long*>(f->w_partial.p), 0ull, cnt);
         }
         const bool multi = streamed && f->chunk_streams;
         if (multi) GGP_CUDA(cudaEventRecord(f->eval_start, f->stream));
@@ -496,13 +564,13 @@ int ggp_loglik(ggp_forest* f, const double* params, int32_t n_vec, double* root_
     // copy engine: small batches travel in the launch arguments instead
     const double* d_params = f->w_params.p;
     f->h_inline_params = nullptr;
-    if (n_vec <= GGP_INLINE_VECS && f->upload_pending && !root_carry) {
+    if (n_vec <= GGP_INLINE_VECS && f->upload_pending && !root_carry && !f->legacy_loglik) {
         f->h_inline_params = params;
         d_params = nullptr;
     } else {
         GGP_CUDA(cudaMemcpyAsync(f->w_params.p, params, (size_t)n_vec * GGP_NP * sizeof(double), cudaMemcpyHostToDevice, s));
     }
-    ggp_fill64_kernel<<<(unsigned)std::min<size_t>(((size_t)n_vec + 255) / 256, 1184), 256, 0, s>>>(f->w_nan.p, ~0ull, (size_t)n_vec);
+    ggp_fill64_kernel<<<f->fill_grid((size_t)n_vec), 256, 0, s>>>(f->w_nan.p, ~0ull, (size_t)n_vec);
     f->last_launches = 0;
     GGP_CUDA(cudaEventRecord(f->ev0, s));
     if (int rc = enqueue_loglik(f, d_params, n_vec, root_carry ? f->w_carry.p : nullptr, f->w_out.p,
@@ -549,7 +617,7 @@ int ggp_loglik_device(ggp_forest* f, const double* d_params, int32_t n_vec, doub
     if (!d_params || !d_out_loglik || n_vec <= 0) return fail(GGP_ERR_BAD_ARG, "bad params/out/n_vec");
     GGP_CUDA(cudaSetDevice(f->device));
     GGP_CUDA(f->w_nan.ensure(n_vec));
-    ggp_fill64_kernel<<<(unsigned)std::min<size_t>(((size_t)n_vec + 255) / 256, 1184), 256, 0, f->stream>>>(f->w_nan.p, ~0ull, (size_t)n_vec);
+    ggp_fill64_kernel<<<f->fill_grid((size_t)n_vec), 256, 0, f->stream>>>(f->w_nan.p, ~0ull, (size_t)n_vec);
     f->last_launches = 0;
     GGP_CUDA(cudaEventRecord(f->ev0, f->stream));
     if (int rc = enqueue_loglik(f, d_params, n_vec, nullptr, d_out_loglik, nullptr, f->w_nan.p)) return rc;

@@ -196,9 +196,16 @@ class Forest:
     def set_stream(self, cuda_stream_ptr):
         _lib.check(self._lib.ggp_forest_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
 
-    def upload_series(self, time_ptr, x_ptr, g_ptr):
-        """Re-upload the measurement arrays from host pointers (pinned memory gives async copies)."""
-        _lib.check(self._lib.ggp_forest_upload_series(self._h, C.c_void_p(time_ptr), C.c_void_p(x_ptr), C.c_void_p(g_ptr)))
+    def upload_series(self, time_ptr, x_ptr, g_ptr, init_f=None, init_r=None):
+        """Re-upload measurement arrays from host pointers (pinned memory gives async copies); a pointer of None / 0 leaves
+        that array as it is.  init_f / init_r: the init_cells statistics of the new measurements (moma_input.h:675-735);
+        None = re-derived by the library (forests created without explicit statistics only)."""
+        fi = ri = None
+        if init_f is not None:
+            fi = (C.c_double * 4)(*[float(v) for v in init_f])
+            ri = (C.c_double * 4)(*[float(v) for v in init_r])
+        _lib.check(self._lib.ggp_forest_upload_series(self._h, C.c_void_p(time_ptr or None), C.c_void_p(x_ptr or None),
+                                                      C.c_void_p(g_ptr or None), fi, ri))
 
     @property
     def last_kernel_ms(self):

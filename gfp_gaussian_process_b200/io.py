@@ -29,7 +29,12 @@ class CSVConfig:
 
 
 def _string2bool(s):
-    return s.strip().lower() in ("true", "1", "yes", "t")
+    """utils.h:20-29: exactly these spellings, anything else is an input error"""
+    if s in ("True", "true", "TRUE", "1"):
+        return True
+    if s in ("False", "false", "FALSE", "0"):
+        return False
+    raise ValueError(f"(string2bool) no valid bool conversion of {s!r}")
 
 
 def read_csv_config(path):
@@ -97,8 +102,13 @@ def read_parameter_file(path):
 
 
 def _remove_last_decimal(s):
-    # ids may be written as "7.0": drop the decimals (moma_input.h get_cell_id)
-    return s.split(".")[0]
+    """moma_input.h:327-347: only a purely numeric tag whose part after the last '.' is all zeros loses its decimals
+    ("7.0" -> "7"); "2.1", "20150624.0.1.5" and "a.b" stay as they are"""
+    if any(not (ch.isdigit() and ch.isascii()) and ch != "." for ch in s):
+        return s
+    if any(ch != "0" for ch in s.split(".")[-1]):
+        return s
+    return str(int(float(s)))   # std::to_string(std::stoi(str)): the leading integer
 
 
 def read_data(path, cfg: CSVConfig = None, noise_model="scaled", division_model="binomial"):
@@ -106,7 +116,9 @@ def read_data(path, cfg: CSVConfig = None, noise_model="scaled", division_model=
     cfg = cfg or CSVConfig()
     with open(path) as fh:
         header = fh.readline().rstrip("\n").split(cfg.delm)
-        idx = {h: i for i, h in enumerate(header)}
+        idx = {}
+        for i, h in enumerate(header):   # get_header_indices (moma_input.h:366-381): trimmed tags, the first occurrence wins
+            idx.setdefault(h.strip(" \t\n\v\f\r"), i)
         for col in [cfg.time_col, cfg.length_col, cfg.fp_col] + cfg.cell_tags + cfg.parent_tags + \
                 ([cfg.segment_col] if cfg.segment_col else []) + ([cfg.filter_col] if cfg.filter_col else []):
             if col not in idx:

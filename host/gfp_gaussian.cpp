@@ -590,7 +590,6 @@ void run_correlation(Session& S, Forest& Fx, std::vector<ParameterSet>& list) {
         whole.reset(new DeviceForest(T, S.devices[0]));
         handle = whole->handle();
     }
-    check(ggp_predict(handle, P.data(), (int32_t)list.size(), nullptr, nullptr, nullptr), "ggp_predict");
     comb.resize((size_t)T.n_ctp() * 20);
     check(ggp_predict(handle, P.data(), (int32_t)list.size(), nullptr, nullptr, comb.data()), "ggp_predict");
     std::vector<double> m14((size_t)T.n_ctp() * 14);

@@ -63,8 +63,11 @@ inline NelderMeadResult nelder_mead(const BatchObjective& obj, std::vector<doubl
         return obj.evaluate(X, record);
     };
     std::vector<double> l(n), u(n), s(n), y0(n);
-    for (int k = 0; k < n; ++k) { l[k] = lb[dims[k]]; u[k] = ub[dims[k]]; s[k] = step[dims[k]]; y0[k] = x0[dims[k]]; }
-    for (int k = 0; k < n; ++k) x0[dims[k]] = std::min(std::max(x0[dims[k]], l[k]), u[k]);
+    // a start value outside its bounds is moved onto the nearest bound before the simplex is built from it
+    for (int k = 0; k < n; ++k) {
+        l[k] = lb[dims[k]]; u[k] = ub[dims[k]]; s[k] = step[dims[k]];
+        y0[k] = x0[dims[k]] = std::min(std::max(x0[dims[k]], l[k]), u[k]);
+    }
 
     // initial simplex
     std::vector<std::vector<double>> P(n + 1, y0);

@@ -77,12 +77,18 @@ int64_t ggp_forest_n_cells(const ggp_forest* f);
 int64_t ggp_forest_n_ctp(const ggp_forest* f);
 int64_t ggp_forest_n_roots(const ggp_forest* f);
 int64_t ggp_forest_n_generations(const ggp_forest* f);
-/* replace the measurement arrays (MOMAdata::time/log_length/fp, [n_ctp] each, same topology) from host memory;
- * the copies are chunked and asynchronous on an internal copy stream when the source is pinned, and the next ggp_loglik
- * starts on a chunk's trees as soon as that chunk has landed (the caller must keep the host arrays alive until that call
- * returns).  The init_cells statistics keep the values of ggp_forest_create.  Used when the same genealogy is evaluated on
- * new measurements (and by bench.py's end-to-end leg). */
-int ggp_forest_upload_series(ggp_forest* f, const double* time, const double* log_length, const double* fp);
+/* replace measurement arrays (MOMAdata::time/log_length/fp, [n_ctp] each, same topology) from host memory; a NULL array
+ * is left as it is (an unchanged time grid need not travel again).  The copies are chunked and asynchronous on an internal
+ * copy stream when the source is pinned, and the next ggp_loglik starts on a chunk's trees as soon as that chunk has landed
+ * (the caller must keep the host arrays alive until that call returns).
+ * The root / leaf priors are statistics of the measurements (init_cells_f/r, moma_input.h:675-735), so new log_length / fp
+ * arrays come with new statistics: pass them (init_f4, init_r4, e.g. from ggp_init_stats over the whole data set), or pass
+ * NULL, NULL to have the library re-derive them from the new arrays - possible only for a forest created with
+ * compute_init = 1 (one host pass over the cells' first and last points); a forest created with the statistics of a larger
+ * data set (compute_init = 0) returns GGP_ERR_BAD_ARG instead of silently keeping stale priors.
+ * Used when the same genealogy is evaluated on new measurements (and by bench.py's end-to-end leg). */
+int ggp_forest_upload_series(ggp_forest* f, const double* time, const double* log_length, const double* fp,
+                             const double* init_f4, const double* init_r4);
 int ggp_forest_get_init(const ggp_forest* f, double* init_f4, double* init_r4);
 /* the init_cells_f / init_cells_r statistics of a data set (moma_input.h:675-735) without creating a forest: what a caller
  * that shards trees over several handles passes to every shard (compute_init = 0).  Host arithmetic on the descriptor's

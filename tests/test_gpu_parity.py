@@ -304,10 +304,11 @@ def test_streamed_upload_evaluates_chunk_by_chunk(chunks, monkeypatch):
         f.upload_series(t2.ctypes.data, x2.ctypes.data, g2.ctypes.data)
         vecs = np.stack([P, P * 1.01])
         ll1, pc1 = ggp.total_likelihood(vecs, f, per_cell=True)
+        # the root / leaf priors follow the NEW measurements (init_cells_f/r, moma_input.h:675-735): the oracle derives its own
         d2 = ggp.LineageData(cell_offset=d.cell_offset, parent=d.parent, time=t2, log_length=x2, fp=g2, segment=d.segment,
-                             noise_model=d.noise_model, division_model=d.division_model, fp_auto=d.fp_auto,
-                             init_f=f.init_stats()[0], init_r=f.init_stats()[1])
+                             noise_model=d.noise_model, division_model=d.division_model, fp_auto=d.fp_auto)
         o = Oracle(d2)
+        assert same_bits(f.init_stats()[0], o.init_stats()[0]) and same_bits(f.init_stats()[1], o.init_stats()[1])
         for i in range(2):
             assert same_bits(pc1[i], o.total_loglik(vecs[i], per_cell=True)[1])
         assert not same_bits(pc1[0], pc0)
@@ -316,12 +317,23 @@ def test_streamed_upload_evaluates_chunk_by_chunk(chunks, monkeypatch):
         # (per-cell sums are identical; the forest total is reduced over different block partials, last-bit differences)
         assert same_bits(pc2, pc1) and max_rel(ll2, ll1) < 1e-14
         # predictions after an upload wait for all chunks
-        f.upload_series(d.time.ctypes.data, d.log_length.ctypes.data, d.fp.ctypes.data)
+        # (only the measurements travel: the time grid is unchanged)
+        f.upload_series(None, d.log_length.ctypes.data, d.fp.ctypes.data)
         pr = ggp.prediction_forward_backward(f, [P] * (int(d.segment.max()) + 1))
-        d.init_f, d.init_r = f.init_stats()
         ref = Oracle(d).predictions([P] * (int(d.segment.max()) + 1))
         assert same_bits(pr["prediction"][0], ref["prediction"][0])
         f.close()
+        # a shard carries the statistics of the whole data set: new measurements must come with new statistics
+        sub, cells, ctp = d.subset(d.roots()[:2])
+        fs = ggp.Forest(sub)
+        with pytest.raises(Exception):
+            fs.upload_series(None, x2[ctp].copy().ctypes.data, None)
+        o2 = Oracle(d2)
+        xs, gs = np.ascontiguousarray(x2[ctp]), np.ascontiguousarray(g2[ctp])
+        fs.upload_series(None, xs.ctypes.data, gs.ctypes.data, *o2.init_stats())
+        sub2, _, _ = d2.subset(d2.roots()[:2])
+        assert same_bits(ggp.total_likelihood(P, fs, per_cell=True)[1], Oracle(sub2).total_loglik(P, per_cell=True)[1])
+        fs.close()
 
 
 @pytest.mark.gpu

@@ -177,3 +177,25 @@ def test_cli_without_gpu_fails_loudly(tmp_path):
     assert r.returncode == 1 and "noise_model must be either" in r.stdout
     r = subprocess.run([CLI, "-h"], capture_output=True, text=True)
     assert r.returncode == 0 and "--parameter_bounds" in r.stdout
+
+
+def test_python_reader_composes_ids_like_the_cpp_reader(hc, tmp_path):
+    """remove_last_decimal (moma_input.h:327-347): only an all-zero fraction of a purely numeric tag is dropped; fractional
+    and dotted tags stay, so '2.1' and '2.2' remain two cells.  Header tags are trimmed; bool spellings are strict."""
+    csv, cfg = str(tmp_path / "in.csv"), str(tmp_path / "cfg.txt")
+    rows = [("7.0", "0"), ("7.0", "0"), ("2.1", "7"), ("2.2", "7.00"), ("20150624.0.1.5", "2.1"), ("a.b", "2.2"), ("10.", "a.b")]
+    with open(csv, "w") as f:
+        f.write("cell_id , parent_id,time,length,gfp,keep\n")
+        for k, (c, p) in enumerate(rows):
+            f.write(f"{c},{p},{k},2.0,10,True\n")
+    open(cfg, "w").write("filter_col = keep\n")
+    got = load(hc, csv, cfg)
+    data, ids = ggio.read_data(csv, ggio.read_csv_config(cfg))
+    assert ids == got["ids"] == ["7", "2.1", "2.2", "20150624.0.1.5", "a.b", "10"]
+    assert np.array_equal(data.parent, got["parent"]) and data.parent.tolist() == [-1, 0, 0, 1, 2, 4]
+    assert np.array_equal(data.cell_offset, got["off"])
+    with open(csv, "a") as f:
+        f.write("11,10,9,2.0,10,yes\n")
+    with pytest.raises(ValueError):
+        ggio.read_data(csv, ggio.read_csv_config(cfg))
+    assert hc.hcli_load(csv.encode(), cfg.encode(), -1) == -1

@@ -11,6 +11,7 @@ LIB_PATH = os.environ.get("GGP_B200_LIB", os.path.join(_HERE, "libggp_b200.so"))
 
 GGP_OK, GGP_ERR_BAD_ARG, GGP_ERR_NAN, GGP_ERR_CUDA, GGP_ERR_NOMEM = range(5)
 N_PARAMS = 11
+GGP_MODE_STRICT, GGP_MODE_FAST = 0, 1
 
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)
@@ -54,6 +55,9 @@ SIGNATURES = {
     "ggp_forest_n_roots": (C.c_int64, [C.c_void_p]),
     "ggp_forest_n_generations": (C.c_int64, [C.c_void_p]),
     "ggp_forest_get_init": (C.c_int, [C.c_void_p, c_double_p, c_double_p]),
+    "ggp_forest_set_mode": (C.c_int, [C.c_void_p, C.c_int32]),
+    "ggp_forest_get_mode": (C.c_int32, [C.c_void_p]),
+    "ggp_last_strict_reruns": (C.c_int64, [C.c_void_p]),
     "ggp_init_stats": (C.c_int, [C.POINTER(ForestDesc), c_double_p, c_double_p]),
     "ggp_loglik": (C.c_int, [C.c_void_p, c_double_p, C.c_int32, c_double_p, c_double_p, c_double_p, C.POINTER(NanInfo)]),
     "ggp_loglik_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),

@@ -22,6 +22,7 @@
 #include "ggp_kernels.cuh"
 #include "ggp_coop_kernels.cuh"
 #include "ggp_joints.cuh"
+#include "ggp_fast_api.h"
 
 // groups per block of the prediction passes: 3 (384 threads, up to 170 registers) keeps their larger per-thread state
 // (segment lookups, output pointers) out of local memory; with 4 groups the 128-register cap spills loop-carried values
@@ -121,6 +122,10 @@ struct ggp_forest {
     int64_t coop_ng4_min_groups = 0;      // launches with at least this many 32-cell groups use 4 groups per block (8 per SM; set at create)
     int coop_variant = 4;                 // GGP_B200_COOP_VARIANT (A/B measurements): 0 = 4 groups/block, block barriers; 2 = 2 groups/block; 3 = 4 groups, per-group barriers
     bool legacy_loglik = false;           // GGP_B200_LEGACY_LOGLIK=1: one-thread-per-cell likelihood kernel (A/B measurements)
+    int fast_nodes = 0;                   // 0 = strict likelihood (bit-exact, the default); N = fast likelihood with an N-node rule
+                                          // (ggp_forest_set_mode / GGP_B200_FAST): not bit-exact, fresh-mode ggp_loglik only
+    int64_t last_reruns = 0;
+    int32_t device_fast_vecs = 0;         // vectors of a fast ggp_loglik_device whose flags ggp_sync_kernel_ms still has to read              // vectors of the last fast ggp_loglik that were re-run on the strict path
     // device
     DevBuf<double> time, x, g;
     DevBuf<int32_t> seg, comb_seg;
@@ -129,6 +134,7 @@ struct ggp_forest {
     // workspaces
     DevBuf<double> w_params, w_state, w_partial, w_out, w_cell_ll, w_carry;
     DevBuf<unsigned long long> w_nan;
+    DevBuf<int> w_invalid;
     DevBuf<double> fwd, bwd, comb, bstate, pred_params, prep, jstack;
     DevBuf<int32_t> ctp_slot, jstack_slot;
     bool have_prep = false;
@@ -277,6 +283,10 @@ int ggp_forest_create(const ggp_forest_desc* d, ggp_forest** out) {
         if (const char* m = getenv("GGP_B200_WALK_BLOCKS")) f->walk_blocks_per_sm = std::max(1, atoi(m));
         if (const char* m = getenv("GGP_B200_WALK_TOTAL_BLOCKS")) f->walk_total_blocks = std::max<int64_t>(0, atoll(m));
         if (const char* m = getenv("GGP_B200_STATE_BUDGET")) f->state_budget_bytes = std::max<int64_t>(1, atoll(m));
+        if (const char* m = getenv("GGP_B200_FAST")) {   // 1 = the default rule, N = an N-node rule
+            const int n = atoi(m);
+            f->fast_nodes = n == 1 ? GGP_FAST_DEFAULT_NODES : (ggp_fast_supported_nodes(n) ? n : 0);
+        }
     }
 
     cudaStream_t s = nullptr;
@@ -345,6 +355,7 @@ void ggp_forest_destroy(ggp_forest* f) {
     f->s_off.release();
     f->s_dfs0.release();
     f->w_nan.release();
+    f->w_invalid.release();
     for (cudaEvent_t ev : f->chunk_ready) if (ev) cudaEventDestroy(ev);
     if (f->compute_done) cudaEventDestroy(f->compute_done);
     if (f->eval_start) cudaEventDestroy(f->eval_start);
@@ -439,6 +450,17 @@ int ggp_init_stats(const ggp_forest_desc* d, double* init_f4, double* init_r4) {
     return GGP_OK;
 }
 
+int ggp_forest_set_mode(ggp_forest* f, int32_t mode) {
+    if (int rc = check_handle(f)) return rc;
+    if (mode == GGP_MODE_STRICT) f->fast_nodes = 0;
+    else if (mode == GGP_MODE_FAST) f->fast_nodes = GGP_FAST_DEFAULT_NODES;
+    else if (ggp_fast_supported_nodes(mode)) f->fast_nodes = mode;
+    else return fail(GGP_ERR_BAD_ARG, "unknown likelihood mode");
+    return GGP_OK;
+}
+int32_t ggp_forest_get_mode(const ggp_forest* f) { return f ? f->fast_nodes : -1; }
+int64_t ggp_last_strict_reruns(const ggp_forest* f) { return f ? f->last_reruns : -1; }
+
 double ggp_last_kernel_ms(const ggp_forest* f) { return f ? f->last_ms : -1.0; }
 int64_t ggp_last_launch_count(const ggp_forest* f) { return f ? f->last_launches : -1; }
 
@@ -455,8 +477,9 @@ int wait_for_upload(ggp_forest* f) {
 }
 
 // enqueue the likelihood of vectors [0, n_vec) held in d_params; results to d_out [n_vec]
+// d_invalid != nullptr: the fast kernels (fresh mode only), which flag the vectors the caller has to re-run strictly
 int enqueue_loglik(ggp_forest* f, const double* d_params, int32_t n_vec, double* d_carry, double* d_out,
-                   double* d_cell_ll, unsigned long long* d_nan) {
+                   double* d_cell_ll, unsigned long long* d_nan, int* d_invalid = nullptr) {
     const int64_t N = f->n_cells;
     int64_t chunk = std::max<int64_t>(1, f->state_budget_bytes / (N * 14 * (int64_t)sizeof(double)));
     chunk = std::min<int64_t>(chunk, n_vec);
@@ -470,6 +493,7 @@ int enqueue_loglik(ggp_forest* f, const double* d_params, int32_t n_vec, double*
     // multi-chunk batches wait for the whole upload)
     const bool streamed = f->upload_pending && K > 1 && !d_carry && chunk >= n_vec && !f->legacy_loglik;
     if (!d_params && (f->legacy_loglik || !f->h_inline_params)) return fail(GGP_ERR_BAD_ARG, "inline parameters without a vector");
+    if (d_invalid && d_carry) return fail(GGP_ERR_BAD_ARG, "the fast likelihood has no carry mode");
     if (!streamed) if (int rc = wait_for_upload(f)) return rc;
     for (int32_t v0 = 0; v0 < n_vec; v0 += (int32_t)chunk) {
         const int32_t vc = (int32_t)std::min<int64_t>(chunk, n_vec - v0);
@@ -506,7 +530,9 @@ int enqueue_loglik(ggp_forest* f, const double* d_params, int32_t n_vec, double*
                 A.nan_key = d_nan;
                 A.out_fwd = nullptr;
                 const int gx = grid_of(A.n_slots);
-                if (g == 0 && d_carry && f->legacy_loglik)
+                if (d_invalid) {
+                    GGP_CUDA(ggp_fast_loglik_launch(F, A, d_invalid, f->fast_nodes, ks));
+                } else if (g == 0 && d_carry && f->legacy_loglik)
                     ggp_forward_kernel<false, true><<<dim3(gx, 1), GGP_BLOCK, GGP_SMEM_BYTES, ks>>>(F, A);
                 else if (g == 0 && d_carry)
                     ggp_loglik_chain_coop_kernel<<<dim3(grid_of_coop(A.n_slots), 1), GGP_COOP_BLOCK(1), GGP_COOP_SMEM_BYTES_CHAIN, ks>>>(F, A);
@@ -555,6 +581,12 @@ int ggp_loglik(ggp_forest* f, const double* params, int32_t n_vec, double* root_
     GGP_CUDA(f->w_params.ensure((size_t)n_vec * GGP_NP));
     GGP_CUDA(f->w_out.ensure(n_vec));
     GGP_CUDA(f->w_nan.ensure(n_vec));
+    const bool fast = f->fast_nodes > 0 && !root_carry && !f->legacy_loglik;
+    f->last_reruns = 0;
+    if (fast) {
+        GGP_CUDA(f->w_invalid.ensure(n_vec));
+        GGP_CUDA(cudaMemsetAsync(f->w_invalid.p, 0, (size_t)n_vec * sizeof(int), s));
+    }
     if (out_cell_ll) GGP_CUDA(f->w_cell_ll.ensure((size_t)n_vec * f->n_cells));
     if (root_carry) {
         GGP_CUDA(f->w_carry.ensure((size_t)f->n_roots * 16));
@@ -574,7 +606,7 @@ int ggp_loglik(ggp_forest* f, const double* params, int32_t n_vec, double* root_
     f->last_launches = 0;
     GGP_CUDA(cudaEventRecord(f->ev0, s));
     if (int rc = enqueue_loglik(f, d_params, n_vec, root_carry ? f->w_carry.p : nullptr, f->w_out.p,
-                                out_cell_ll ? f->w_cell_ll.p : nullptr, f->w_nan.p))
+                                out_cell_ll ? f->w_cell_ll.p : nullptr, f->w_nan.p, fast ? f->w_invalid.p : nullptr))
         return rc;
     GGP_CUDA(cudaEventRecord(f->ev1, s));
     GGP_CUDA(cudaMemcpyAsync(out_loglik, f->w_out.p, (size_t)n_vec * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -584,10 +616,43 @@ int ggp_loglik(ggp_forest* f, const double* params, int32_t n_vec, double* root_
         GGP_CUDA(cudaMemcpyAsync(out_cell_ll, f->w_cell_ll.p, (size_t)n_vec * f->n_cells * sizeof(double), cudaMemcpyDeviceToHost, s));
     if (root_carry)
         GGP_CUDA(cudaMemcpyAsync(root_carry, f->w_carry.p, (size_t)f->n_roots * 16 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    std::vector<int> invalid;
+    if (fast) {
+        invalid.resize(n_vec);
+        GGP_CUDA(cudaMemcpyAsync(invalid.data(), f->w_invalid.p, (size_t)n_vec * sizeof(int), cudaMemcpyDeviceToHost, s));
+    }
     GGP_CUDA(cudaStreamSynchronize(s));
     float ms = 0.f;
     GGP_CUDA(cudaEventElapsedTime(&ms, f->ev0, f->ev1));
     f->last_ms = ms;
+    if (fast) {
+        // vectors whose evaluation left the quadrature's validity range (or met a NaN term) are evaluated again on the
+        // strict path: their results, NaN records and per-cell sums are the strict ones
+        std::vector<int32_t> redo;
+        for (int32_t v = 0; v < n_vec; ++v) if (invalid[v]) redo.push_back(v);
+        if (!redo.empty()) {
+            const int64_t launches = f->last_launches;
+            std::vector<double> P(redo.size() * GGP_NP), ll(redo.size()), cl(out_cell_ll ? redo.size() * (size_t)f->n_cells : 0);
+            std::vector<ggp_nan_info> ni(redo.size());
+            for (size_t i = 0; i < redo.size(); ++i) std::memcpy(&P[i * GGP_NP], params + (size_t)redo[i] * GGP_NP, GGP_NP * sizeof(double));
+            const int keep = f->fast_nodes;
+            f->fast_nodes = 0;
+            const int rc = ggp_loglik(f, P.data(), (int32_t)redo.size(), nullptr, ll.data(), out_cell_ll ? cl.data() : nullptr, ni.data());
+            f->fast_nodes = keep;
+            f->last_ms += ms;
+            f->last_launches += launches;
+            f->last_reruns = (int64_t)redo.size();
+            if (rc != GGP_OK && rc != GGP_ERR_NAN) return rc;
+            for (int32_t v = 0; v < n_vec; ++v) if (nan) { nan[v].cell = -1; nan[v].t_index = -1; }
+            for (size_t i = 0; i < redo.size(); ++i) {
+                out_loglik[redo[i]] = ll[i];
+                if (nan) nan[redo[i]] = ni[i];
+                if (out_cell_ll) std::memcpy(out_cell_ll + (size_t)redo[i] * f->n_cells, &cl[i * (size_t)f->n_cells], (size_t)f->n_cells * sizeof(double));
+            }
+            if (rc == GGP_ERR_NAN) return fail(GGP_ERR_NAN, "Likelihood is Nan");
+            return GGP_OK;
+        }
+    }
     if (f->timeline && f->tl_upload0 && cudaEventQuery(f->tl_begin[0]) == cudaSuccess && cudaEventQuery(f->tl_upload0) == cudaSuccess) {
         for (int k = 0; k < f->L.n_chunks; ++k) {
             float a = 0, b = 0, c = 0;
@@ -619,8 +684,14 @@ int ggp_loglik_device(ggp_forest* f, const double* d_params, int32_t n_vec, doub
     GGP_CUDA(f->w_nan.ensure(n_vec));
     ggp_fill64_kernel<<<f->fill_grid((size_t)n_vec), 256, 0, f->stream>>>(f->w_nan.p, ~0ull, (size_t)n_vec);
     f->last_launches = 0;
+    const bool fast = f->fast_nodes > 0 && !f->legacy_loglik;
+    if (fast) {   // the flags are checked by ggp_sync_kernel_ms
+        GGP_CUDA(f->w_invalid.ensure(n_vec));
+        ggp_fill64_kernel<<<f->fill_grid(((size_t)n_vec + 1) / 2), 256, 0, f->stream>>>(reinterpret_cast<unsigned long long*>(f->w_invalid.p), 0ull, ((size_t)n_vec + 1) / 2);
+    }
+    f->device_fast_vecs = fast ? n_vec : 0;
     GGP_CUDA(cudaEventRecord(f->ev0, f->stream));
-    if (int rc = enqueue_loglik(f, d_params, n_vec, nullptr, d_out_loglik, nullptr, f->w_nan.p)) return rc;
+    if (int rc = enqueue_loglik(f, d_params, n_vec, nullptr, d_out_loglik, nullptr, f->w_nan.p, fast ? f->w_invalid.p : nullptr)) return rc;
     GGP_CUDA(cudaEventRecord(f->ev1, f->stream));
     return GGP_OK;
 }
@@ -633,6 +704,13 @@ int ggp_sync_kernel_ms(ggp_forest* f, double* ms_out) {
     GGP_CUDA(cudaEventElapsedTime(&ms, f->ev0, f->ev1));
     f->last_ms = ms;
     if (ms_out) *ms_out = ms;
+    if (f->device_fast_vecs > 0) {   // a fast evaluation enqueued by ggp_loglik_device: was every vector inside the validity range?
+        std::vector<int> invalid((size_t)f->device_fast_vecs);
+        GGP_CUDA(cudaMemcpy(invalid.data(), f->w_invalid.p, invalid.size() * sizeof(int), cudaMemcpyDeviceToHost));
+        f->device_fast_vecs = 0;
+        for (int v : invalid)
+            if (v) return fail(GGP_ERR_BAD_ARG, "fast likelihood: a parameter vector left the quadrature's validity range; evaluate it with ggp_loglik (which re-runs it strictly)");
+    }
     return GGP_OK;
 }
 

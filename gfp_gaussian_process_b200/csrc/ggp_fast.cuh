@@ -1,0 +1,302 @@
+// ggp_fast.cuh — the FAST likelihood step: same model and same moments as mean_cov_model() (reference
+// src/mean_cov_model.h:73-274), different evaluation, NOT bit-identical to the reference.  Log-likelihood only
+// (-m, -s, BASELINE configs[1] and [3]); predictions and joints stay on the strict path.
+//
+// Why it exists: the strict path reproduces the reference's rounding bit for bit, which costs
+// 66 exp + 14 Dawson + 3 pow per step, forbids FMA, and keeps the reference's ill-conditioning (integrals formed as
+// differences of exp * Dawson products divided by a^(k+1/2), a = C_ll / 2 ~ 3e-7; covariances as raw second moments minus
+// squared means).  Here:
+//   * the integrals  I_k(B, c; t0, t1) = int s^k exp(a s^2 + B s + c) ds  are evaluated by Gauss-Legendre quadrature.  The
+//     integrand is entire and nearly linear in the exponent over one time step (|a t^2 + B t| ~ 1e-2 on real data), so N
+//     nodes integrate it to rounding error; every term of the sum is positive: no cancellation, no Dawson function, no
+//     division by powers of a.  All 39 integrals of a step share 3 N exponentials: exp(a s^2 + B0 s), exp(a s^2 + W s) on
+//     [0, t] and exp(a s'^2 + W s') on [t, 2t]; the -gq / +gq variants and the nine constants c only multiply these by
+//     factors that depend on the parameters and dt alone (cached while dt repeats).
+//   * the g-row of the new covariance is written in CENTRAL form.  With  G1 = mq J_B[0] + dq J_Bm[0] + Clq J_Bm[1]
+//     (the production integral: mean_g = bg e^{-b t} + G1), G2 the same with one more power of s, dq = bq + Cxq - mq:
+//         cov(g, y) = e^{-gamma_y t} (e^{-b t} C_gy + C_xy G1 + C_ly G2 + C_qy J_Bm[0] [+ OU noise term for y = q])
+//     for y = lambda, q, and the analogous x row; cov_gg = C_gg e^{-2bt} + 2 e^{-bt} (C_xg G1 + C_gl G2 + C_gq J_Bm[0])
+//     + S2 - G1^2.  These are the reference's formulas (mean_cov_model.h:97-192) with the "- nm(1) * nm(i)" products expanded
+//     and cancelled analytically; algebraically identical, far better conditioned.
+//   * FMA contraction is allowed (this header is compiled with -fmad=true), exp / log are the CUDA library's.
+// Accuracy: differs from the reference by the reference's own rounding noise (tools/ulp_envelope.py measures that
+// envelope); the gate is |dloglik| / |loglik| <= 1e-10 against the oracle (tests/test_gpu_fast.py), and
+// tests/hostcheck/fastcheck.cpp compares both with a binary128 evaluation.
+// Validity: the quadrature order N is fixed at compile time; a step whose exponent varies by more than GGP_FAST_LMAX over
+// the step (or whose C_ll is negative / not finite) raises the evaluation's `invalid` flag and the caller re-runs that
+// parameter vector on the strict path.
+//
+// Templated on the scalar type so that the same code runs in binary128 on the host (the "truth" of the gate report).
+#pragma once
+#include "ggp_types.cuh"
+#include "ggp_gl_tables.h"
+
+#ifndef GGP_FAST_N
+#define GGP_FAST_N 6
+#endif
+
+template <class T> struct GgpFx;   // scalar helpers
+template <> struct GgpFx<double> {
+    static GGP_HDM double exp_(double x) { return exp(x); }
+    static GGP_HDM double log_(double x) { return log(x); }
+    static GGP_HDM double expm1_(double x) { return expm1(x); }
+    static GGP_HDM double abs_(double x) { return fabs(x); }
+    static GGP_HDM bool finite_(double x) { return x - x == 0.0; }
+    static GGP_HDM double ln2() { return 0.6931471805599453; }
+};
+
+// largest |d(exponent)/ds| * t a step may have for the N-node rule to integrate s^k exp(lambda s), k = 0..3, over [0, t] and
+// [t, 2t] to 3e-15 relative (measured against mpmath)
+template <int N> struct GgpFastLmax;
+template <> struct GgpFastLmax<3> { static GGP_HDM constexpr double v() { return 0.004; } };
+template <> struct GgpFastLmax<4> { static GGP_HDM constexpr double v() { return 0.02; } };
+template <> struct GgpFastLmax<5> { static GGP_HDM constexpr double v() { return 0.12; } };
+template <> struct GgpFastLmax<6> { static GGP_HDM constexpr double v() { return 0.5; } };
+template <> struct GgpFastLmax<8> { static GGP_HDM constexpr double v() { return 1.8; } };
+template <> struct GgpFastLmax<10> { static GGP_HDM constexpr double v() { return 4.0; } };
+template <> struct GgpFastLmax<12> { static GGP_HDM constexpr double v() { return 6.0; } };
+template <> struct GgpFastLmax<16> { static GGP_HDM constexpr double v() { return 10.0; } };
+
+// the N-node rule as an object (host checks pass a binary128 rule instead)
+template <int N>
+struct GgpGLRule {
+    GGP_HDM double xi(int j) const { return GgpGL<N>::xi(j); }
+    GGP_HDM double om(int j) const { return GgpGL<N>::om(j); }
+};
+
+template <class T>
+struct GgpFastState {
+    T m[4];    // mean: x, g, lambda, q
+    T c[10];   // covariance, upper triangle row-major: xx xg xl xq gg gl gq ll lq qq
+};
+
+// what depends on the parameters and dt only; recomputed when dt changes
+template <class T, int N>
+struct GgpFastConsts {
+    T t;                          // the dt these were computed for
+    T ebt, egl, egq, epgq;        // exp(-b t), exp(-gl t), exp(-gq t), exp(+gq t)
+    T igl, igq, oi;               // 1/gl, 1/gq, (1 - exp(-gl t)) / gl
+    T kxx, kxl, kll, kqq;         // OU noise contributions to cov_xx, cov_xl, cov_ll, cov_qq
+    T s[N], w[N];                 // nodes t xi_j and weights t om_j
+    T R[N], Rp[N];                // exp(-gq s_j), exp(+gq s_j)
+};
+
+template <class T, int N, class GL>
+GGP_HD void ggp_fast_consts(GgpFastConsts<T, N>& K, T t, T ml, T gl, T sl2, T mq, T gq, T sq2, T b, const GL& gln) {
+    typedef GgpFx<T> X;
+    (void)ml; (void)mq;
+    K.t = t;
+    K.ebt = X::exp_(-b * t);
+    K.egl = X::exp_(-gl * t);
+    K.egq = X::exp_(-gq * t);
+    K.epgq = X::exp_(gq * t);
+    K.igl = T(1) / gl;
+    K.igq = T(1) / gq;
+    const T omegl = -X::expm1_(-gl * t);
+    K.oi = omegl * K.igl;
+    // mean_cov_model.h:93-95, 117-119, 196-208: the terms without state
+    K.kxx = sl2 * T(0.5) * K.igl * K.igl * K.igl * (T(2) * gl * t + T(4) * X::expm1_(-gl * t) - X::expm1_(T(-2) * gl * t));
+    K.kxl = sl2 * T(0.5) * K.oi * K.oi;
+    K.kll = sl2 * T(0.5) * K.igl * (-X::expm1_(T(-2) * gl * t));
+    K.kqq = sq2 * T(0.5) * K.igq * (-X::expm1_(T(-2) * gq * t));
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        K.s[j] = t * gln.xi(j);
+        K.w[j] = t * gln.om(j);
+        K.R[j] = X::exp_(-gq * K.s[j]);
+        K.Rp[j] = X::exp_(gq * K.s[j]);
+    }
+}
+
+// one propagation step over K.t; returns false if the step is outside the quadrature's validity range
+template <class T, int N>
+GGP_HD bool ggp_fast_propagate(GgpFastState<T>& st, const GgpFastConsts<T, N>& K, T ml, T gl, T mq, T gq, T sq2, T b, T lmax) {
+    typedef GgpFx<T> X;
+    (void)gl;
+    const T bx = st.m[0], bg = st.m[1], bl = st.m[2], bq = st.m[3];
+    const T Cxx = st.c[0], Cxg = st.c[1], Cxl = st.c[2], Cxq = st.c[3], Cgg = st.c[4], Cgl = st.c[5], Cgq = st.c[6],
+            Cll = st.c[7], Clq = st.c[8], Cqq = st.c[9];
+    const T t = K.t;
+    const T a = T(0.5) * Cll;
+    const T B0 = b + bl + Cxl, W = B0 + Cxl;
+    // validity of the rule: the exponent a s^2 + B s, B in {B0, W} -+ gq, over [0, 2t]
+    const T lam = (X::abs_(B0) > X::abs_(W) ? X::abs_(B0) : X::abs_(W)) + X::abs_(gq) + T(4) * X::abs_(a) * t;
+    const bool ok = (a >= T(0)) && X::finite_(lam) && (lam * t <= lmax);
+
+    // ---- the 19 moments of the step: sum_j w_j s_j^k * (exponential), mean_cov_model.h:9-67 by quadrature ----
+    T MB0 = 0, MB1 = 0, MBm0 = 0, MBm1 = 0, MBm2 = 0, MBs0 = 0;         // [0,t]: B0; B0 - gq; (B0 + gq) - (B0 - gq)
+    T MW0 = 0, MW1 = 0, MWm0 = 0, MWm1 = 0, MWm2 = 0, MWm3 = 0;        // [0,t]: W; W - gq
+    T NW0 = 0, NW1 = 0, NWm0 = 0, NWm1 = 0, NWm2 = 0, NWm3 = 0, NWp0 = 0;   // [t,2t]: W; W - gq; W + gq
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        const T s = K.s[j], w = K.w[j], sh = t + s;
+        const T A = X::exp_(s * (B0 + a * s));
+        const T AW = X::exp_(s * (W + a * s));
+        const T H = X::exp_(sh * (W + a * sh));
+        const T wa = w * A, war = wa * K.R[j];
+        MB0 += wa; MB1 += wa * s;
+        MBm0 += war; MBm1 += war * s; MBm2 += war * (s * s);
+        MBs0 += wa * (K.Rp[j] - K.R[j]);
+        const T ww = w * AW, wwr = ww * K.R[j];
+        MW0 += ww; MW1 += ww * s;
+        MWm0 += wwr; MWm1 += wwr * s; MWm2 += wwr * (s * s); MWm3 += wwr * (s * s * s);
+        const T wh = w * H, whr = wh * (K.R[j] * K.egq);
+        NW0 += wh; NW1 += wh * sh;
+        NWm0 += whr; NWm1 += whr * sh; NWm2 += whr * (sh * sh); NWm3 += whr * (sh * sh * sh);
+        NWp0 += wh * (K.Rp[j] * K.epgq);
+    }
+    // exp(c): c0 = bx + Cxx/2 - b t (B-family, mean_cov_model.h:76-115), c5 = 2 (bx + Cxx - b t) (W-family, :124-164)
+    const T Ec0 = X::exp_(bx + T(0.5) * Cxx) * K.ebt;
+    const T Ec5 = X::exp_(T(2) * (bx + Cxx)) * (K.ebt * K.ebt);
+    const T JB0 = Ec0 * MB0, JB1 = Ec0 * MB1;                          // I_k(B0, c0; 0, t)
+    const T JBm0 = Ec0 * MBm0, JBm1 = Ec0 * MBm1, JBm2 = Ec0 * MBm2;   // I_k(B0 - gq, c0; 0, t)
+    const T JBs0 = Ec0 * MBs0;                                         // I_0(B0 + gq, c0) - I_0(B0 - gq, c0)
+    const T L0 = Ec5 * MW0, L1 = Ec5 * MW1, Lh0 = Ec5 * NW0, Lh1 = Ec5 * NW1;
+    const T Q0 = Ec5 * MWm0, Q1 = Ec5 * MWm1, Q2 = Ec5 * MWm2, Q3 = Ec5 * MWm3;
+    const T Qh0 = Ec5 * NWm0, Qh1 = Ec5 * NWm1, Qh2 = Ec5 * NWm2, Qh3 = Ec5 * NWm3;
+    const T Ph0 = Ec5 * NWp0;
+
+    const T dq = bq + Cxq - mq;
+    const T G1 = mq * JB0 + dq * JBm0 + Clq * JBm1;   // mean_g - bg e^{-bt}, mean_cov_model.h:76-80
+    const T G2 = mq * JB1 + dq * JBm1 + Clq * JBm2;
+    const T ebt = K.ebt, egl = K.egl, egq = K.egq, oi = K.oi, igq = K.igq;
+
+    // means, mean_cov_model.h:73-87
+    const T nm0 = bx + ml * t + (bl - ml) * oi;
+    const T nm1 = bg * ebt + G1;
+    const T nm2 = ml + (bl - ml) * egl;
+    const T nm3 = mq + (bq - mq) * egq;
+
+    // x row: cov(x_t, .) with x_t = x_0 + int lambda; alpha, beta, gamma = cov(x_t, x_0 / lambda_0 / q_0)
+    const T al = Cxx + Cxl * oi, be = Cxl + Cll * oi, ga = Cxq + Clq * oi;
+    const T n_xx = Cxx + T(2) * Cxl * oi + Cll * (oi * oi) + K.kxx;           // :93-95
+    const T n_xg = ebt * (Cxg + Cgl * oi) + al * G1 + be * G2 + ga * JBm0;    // :97-115, central form
+    const T n_xl = be * egl + K.kxl;                                          // :117-119
+    const T n_xq = ga * egq;                                                  // :120-122
+    // lambda and q rows
+    const T n_gl = egl * (ebt * Cgl + Cxl * G1 + Cll * G2 + Clq * JBm0);      // :166-176, central form
+    const T n_gq = egq * (ebt * Cgq + Cxq * G1 + Clq * G2 + Cqq * JBm0 + sq2 * T(0.5) * igq * JBs0);   // :178-192, central form
+    const T n_ll = Cll * (egl * egl) + K.kll;                                 // :196-198
+    const T n_lq = Clq * egl * egq;                                           // :200-202
+    const T n_qq = Cqq * (egq * egq) + K.kqq;                                 // :204-208
+    // cov_gg, :124-164: C_gg e^{-2bt} + 2 e^{-bt} cov(g_0, production) + E[production^2] - G1^2
+    const T e2 = bq + T(2) * Cxq - mq;
+    const T v2 = e2 * e2 + Cqq;
+    const T cm = T(2) * Clq * mq * igq;         // 2 Clq mq / gq
+    const T me = T(2) * mq * e2 * igq;          // (2 bq mq + 4 Cxq mq - 2 mq^2) / gq
+    const T hs = sq2 * T(0.5) * igq;            // sq2 / (2 gq)
+    const T S2 =
+        (cm + mq * mq) * L1 + (v2 - cm - hs) * Q1 - (mq * mq + cm * egq) * Lh1
+        + (hs - v2 + T(4) * Clq * t * e2 + cm * K.epgq) * Qh1
+        + (Clq * Clq) * (Q3 - Qh3)
+        + T(2) * Clq * e2 * Q2 + T(2) * Clq * (Clq * t - e2) * Qh2
+        + (me + hs * igq) * L0 - (me + hs * igq) * Q0
+        + (hs * igq + T(2) * mq * mq * t - me * egq) * Lh0
+        + (T(2) * t * v2 - sq2 * t * igq + me * K.epgq) * Qh0
+        - hs * igq * (egq * egq) * Ph0;
+    const T n_gg = Cgg * (ebt * ebt) + T(2) * ebt * (Cxg * G1 + Cgl * G2 + Cgq * JBm0) + (S2 - G1 * G1);
+
+    st.m[0] = nm0; st.m[1] = nm1; st.m[2] = nm2; st.m[3] = nm3;
+    st.c[0] = n_xx; st.c[1] = n_xg; st.c[2] = n_xl; st.c[3] = n_xq; st.c[4] = n_gg;
+    st.c[5] = n_gl; st.c[6] = n_gq; st.c[7] = n_ll; st.c[8] = n_lq; st.c[9] = n_qq;
+    return ok;
+}
+
+// measurement update and log-evidence term (likelihood.h:26-32, 53-69, predictions.h:84-89), symmetric covariance
+template <class T>
+GGP_HD T ggp_fast_update(GgpFastState<T>& s, T x, T g, T var_x, T var_g, bool noise_scaled, T fp_auto) {
+    typedef GgpFx<T> X;
+    const T r0 = x - s.m[0], r1 = g - s.m[1];
+    const T D11 = noise_scaled ? var_g * (s.m[1] + fp_auto) : var_g;
+    const T S00 = s.c[0] + var_x, S01 = s.c[1], S11 = s.c[4] + D11;
+    const T det = S00 * S11 - S01 * S01;
+    const T id = T(1) / det;
+    const T Si00 = S11 * id, Si01 = -S01 * id, Si11 = S00 * id;
+    const T q0 = Si00 * r0 + Si01 * r1, q1 = Si01 * r0 + Si11 * r1;   // Si r
+    const T ll = T(-0.5) * (r0 * q0 + r1 * q1) - T(0.5) * X::log_(det) - T(3.6757541328186907);   // 2 log(2 pi) as likelihood.h:31 writes it
+    // K = C[0:2, :]: rows (xx xg xl xq), (xg gg gl gq); T_i = K_i^T Si
+    const T K0[4] = {s.c[0], s.c[1], s.c[2], s.c[3]};
+    const T K1[4] = {s.c[1], s.c[4], s.c[5], s.c[6]};
+    T T0[4], T1[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        T0[i] = K0[i] * Si00 + K1[i] * Si01;
+        T1[i] = K0[i] * Si01 + K1[i] * Si11;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s.m[i] += T0[i] * r0 + T1[i] * r1;
+    T n[10];
+    n[0] = s.c[0] - (T0[0] * K0[0] + T1[0] * K1[0]);
+    n[1] = s.c[1] - (T0[0] * K0[1] + T1[0] * K1[1]);
+    n[2] = s.c[2] - (T0[0] * K0[2] + T1[0] * K1[2]);
+    n[3] = s.c[3] - (T0[0] * K0[3] + T1[0] * K1[3]);
+    n[4] = s.c[4] - (T0[1] * K0[1] + T1[1] * K1[1]);
+    n[5] = s.c[5] - (T0[1] * K0[2] + T1[1] * K1[2]);
+    n[6] = s.c[6] - (T0[1] * K0[3] + T1[1] * K1[3]);
+    n[7] = s.c[7] - (T0[2] * K0[2] + T1[2] * K1[2]);
+    n[8] = s.c[8] - (T0[2] * K0[3] + T1[2] * K1[3]);
+    n[9] = s.c[9] - (T0[3] * K0[3] + T1[3] * K1[3]);
+#pragma unroll
+    for (int i = 0; i < 10; ++i) s.c[i] = n[i];
+    return ll;
+}
+
+// mother's last posterior, already propagated over the gap -> daughter's prior (predictions.h:18-61)
+template <class T>
+GGP_HD void ggp_fast_divide(GgpFastState<T>& s, T var_dx, T var_dg, bool binomial) {
+    if (binomial) {
+        const T c01 = s.m[1] * T(0.5) * var_dx + s.c[1];
+        const T c11 = var_dx * (s.m[1] * s.m[1] + s.c[4]) * T(0.5) + var_dg * s.m[1] * T(0.25) * (T(1) - var_dx) + s.c[4] * T(0.25);
+        s.c[0] += var_dx; s.c[1] = c01; s.c[4] = c11;
+        s.c[5] *= T(0.5); s.c[6] *= T(0.5);
+    } else {
+        s.c[0] += var_dx; s.c[1] *= T(0.5); s.c[4] = var_dg + T(0.25) * s.c[4];
+        s.c[5] *= T(0.5); s.c[6] *= T(0.5);
+    }
+    s.m[0] -= GgpFx<T>::ln2();
+    s.m[1] *= T(0.5);
+}
+
+// ---- one cell of the likelihood (sc_likelihood, likelihood.h:36-103), fresh mode ------------------------------------
+// s: in = the mother's end-of-cell posterior (ignored for a root), out = this cell's.  Returns the cell's log-evidence sum;
+// clears `valid` if a step left the quadrature's range or a term is NaN (the caller then re-runs the vector strictly).
+template <class T, int N, class GL>
+GGP_HD T ggp_fast_cell(const GgpDevForest& F, int slot, const T* __restrict__ p, GgpFastState<T>& s, GgpFastConsts<T, N>& K,
+                       const GL& gln, bool& valid) {
+    const int64_t off = F.s_off[slot];
+    const int n = F.s_n[slot];
+    const int parent = F.s_parent[slot];
+    const bool scaled = F.model.noise_scaled != 0, binomial = F.model.division_binomial != 0;
+    const T fp_auto = T(F.model.fp_auto), lmax = T(GgpFastLmax<N>::v());
+    T own = T(0);
+    int t;
+    int64_t from;
+    if (parent < 0) {   // init_sc_distribution, predictions.h:63-78 (first evaluation: off-diagonals are zero)
+        s.m[0] = T(F.init_f[0]); s.m[1] = T(F.init_f[1]); s.m[2] = p[0]; s.m[3] = p[3];
+#pragma unroll
+        for (int i = 0; i < 10; ++i) s.c[i] = T(0);
+        s.c[0] = T(F.init_f[2]); s.c[4] = T(F.init_f[3]);
+        s.c[7] = p[2] / (T(2) * p[1]);
+        s.c[9] = p[5] / (T(2) * p[4]);
+        const T ll = ggp_fast_update(s, T(F.x[off]), T(F.g[off]), p[7], p[8], scaled, fp_auto);
+        own += ll;
+        if (ll != ll) valid = false;
+        t = 0;
+        from = off;
+    } else {
+        t = -1;
+        from = F.s_off[parent] + F.s_n[parent] - 1;
+    }
+    while (t + 1 < n) {
+        const T dt = T(F.time[off + t + 1]) - T(F.time[from]);
+        if (!(dt == K.t)) ggp_fast_consts(K, dt, p[0], p[1], p[2], p[3], p[4], p[5], p[6], gln);
+        if (!ggp_fast_propagate(s, K, p[0], p[1], p[3], p[4], p[5], p[6], lmax)) valid = false;
+        if (t < 0) ggp_fast_divide(s, p[9], p[10], binomial);
+        ++t;
+        from = off + t;
+        const T ll = ggp_fast_update(s, T(F.x[from]), T(F.g[from]), p[7], p[8], scaled, fp_auto);
+        own += ll;
+        if (ll != ll) valid = false;
+    }
+    return own;
+}

@@ -19,11 +19,6 @@
 #define GGP_TWO_LOG_2PI 3.6757541328186907   /* 2*log(2*M_PI), likelihood.h:31 (same bits from libm and MPFR) */
 #define GGP_LOG2 0.6931471805599453          /* log(2.), predictions.h:37,205 */
 
-struct GgpModel {          // what MOMAdata carries besides data (moma_input.h:44-47)
-    int noise_scaled;      // noise_model == "scaled"
-    int division_binomial; // cell_division_model == "binomial"
-    double fp_auto;
-};
 
 struct GgpMeas {
     double xg0, xg1;

@@ -193,6 +193,20 @@ class Forest:
         _lib.check(self._lib.ggp_forest_get_init(self._h, f4.ctypes.data_as(_lib.c_double_p), r4.ctypes.data_as(_lib.c_double_p)))
         return f4, r4
 
+    def set_mode(self, mode):
+        """likelihood arithmetic: "strict" (bit-exact, default), "fast" (quadrature + FMA, gate 1e-10) or a node count"""
+        code = {"strict": _lib.GGP_MODE_STRICT, "fast": _lib.GGP_MODE_FAST}.get(mode, mode)
+        _lib.check(self._lib.ggp_forest_set_mode(self._h, int(code)))
+
+    @property
+    def mode(self):
+        n = self._lib.ggp_forest_get_mode(self._h)
+        return "strict" if n == 0 else f"fast{n}"
+
+    @property
+    def last_strict_reruns(self):
+        return self._lib.ggp_last_strict_reruns(self._h)
+
     def set_stream(self, cuda_stream_ptr):
         _lib.check(self._lib.ggp_forest_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
 

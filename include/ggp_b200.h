@@ -33,6 +33,17 @@ enum {
 enum { GGP_NOISE_CONST = 0, GGP_NOISE_SCALED = 1 };       /* MOMAdata::noise_model, likelihood.h:59-64 */
 enum { GGP_DIVISION_GAUSS = 0, GGP_DIVISION_BINOMIAL = 1 }; /* MOMAdata::cell_division_model, predictions.h:40-60 */
 
+/* likelihood arithmetic of a handle (ggp_forest_set_mode).
+ * STRICT (default): every result is bit-identical to the reference's own arithmetic (same operation order, glibc's exp /
+ *   pow / log bits, no FMA): the path every parity claim is made on; predictions and joints always use it.
+ * FAST: ggp_loglik / ggp_loglik_device without root_carry only.  Same model, same moments, evaluated by Gauss-Legendre
+ *   quadrature of the integrals of mean_cov_model.h:9-67 and centred covariance formulas, FMA allowed: NOT bit-identical;
+ *   it differs from the reference by the reference's own rounding noise (|dloglik| / |loglik| <= 1e-10 is the gate,
+ *   DESIGN.md).  A parameter vector whose time steps leave the rule's validity range, or that meets a NaN term, is re-run
+ *   on the strict path inside ggp_loglik, so NaN reports are always the reference's.
+ * A value N in {4, 5, 6, 8, 10} selects the fast mode with an N-node rule (GGP_MODE_FAST = 6 nodes). */
+enum { GGP_MODE_STRICT = 0, GGP_MODE_FAST = 1 };
+
 typedef struct ggp_forest ggp_forest;
 
 /* The data the path reads from std::vector<MOMAdata> (moma_input.h:22-80), flattened to SoA.
@@ -90,6 +101,12 @@ int64_t ggp_forest_n_generations(const ggp_forest* f);
 int ggp_forest_upload_series(ggp_forest* f, const double* time, const double* log_length, const double* fp,
                              const double* init_f4, const double* init_r4);
 int ggp_forest_get_init(const ggp_forest* f, double* init_f4, double* init_r4);
+/* likelihood arithmetic of this handle: GGP_MODE_STRICT (default), GGP_MODE_FAST, or a node count (see above); also set by
+ * the environment variable GGP_B200_FAST at ggp_forest_create */
+int ggp_forest_set_mode(ggp_forest* f, int32_t mode);
+int32_t ggp_forest_get_mode(const ggp_forest* f);   /* 0 = strict, else the fast mode's node count */
+/* number of parameter vectors of the last fast ggp_loglik that were re-run on the strict path */
+int64_t ggp_last_strict_reruns(const ggp_forest* f);
 /* the init_cells_f / init_cells_r statistics of a data set (moma_input.h:675-735) without creating a forest: what a caller
  * that shards trees over several handles passes to every shard (compute_init = 0).  Host arithmetic on the descriptor's
  * arrays (input preparation, not part of the device path). */

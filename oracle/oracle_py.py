@@ -63,6 +63,33 @@ def use_reference_math(flag=True):
     return True
 
 
+ORACLE_ULP_SO = os.path.join(_HERE, "_ref", "libggp_oracle_ulp.so")
+
+
+def _configure(L):
+    L.ggp_oracle_dawson.restype = C.c_double
+    L.ggp_oracle_dawson.argtypes = [C.c_double]
+    L.ggp_oracle_tauint.restype = C.c_double
+    L.ggp_oracle_tauint.argtypes = [C.c_int] + [C.c_double] * 5
+    L.ggp_oracle_total_loglik.restype = C.c_double
+    L.ggp_oracle_total_loglik.argtypes = [C.POINTER(OracleForest), dp, dp, dp, dp, lp, lp]
+    if hasattr(L, 'ggp_oracle_joints'):
+        L.ggp_oracle_joints.restype = C.c_long
+    return L
+
+
+def oracle_ulp():
+    """the oracle's loop around the reference core with every exp / pow / Dawson result moved +-1 ulp
+    (oracle/_ref/libggp_oracle_ulp.so; ggp_ref_set_ulp_seed(seed), seed 0 = untouched); None if it cannot be built"""
+    if not os.path.exists(ORACLE_ULP_SO):
+        if not os.path.exists("/root/reference/src/mean_cov_model.h"):
+            return None
+        subprocess.check_call(["make", "-s", "-C", _HERE, "_ref/libggp_oracle_ulp.so"])
+    L = _configure(C.CDLL(ORACLE_ULP_SO))
+    L.ggp_ref_set_ulp_seed.argtypes = [C.c_ulonglong]
+    return L
+
+
 def oracle():
     global _oracle
     if _oracle is None:
@@ -110,8 +137,8 @@ def _p(a, t=dp):
 class Oracle:
     """the oracle bound to one LineageData-like object (any object with the same attribute names)."""
 
-    def __init__(self, data):
-        self.L = oracle()
+    def __init__(self, data, lib=None):
+        self.L = lib if lib is not None else oracle()
         self.data = data
         self._keep = dict(
             off=np.ascontiguousarray(data.cell_offset, dtype=np.int64), parent=np.ascontiguousarray(data.parent, dtype=np.int32),

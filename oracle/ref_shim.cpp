@@ -36,7 +36,39 @@ struct MOMAdata {
     Eigen::MatrixXd cov;
 };
 
+#ifdef GGP_REF_ULP_PERTURB
+// +-1 ulp envelope build (tools/ulp_envelope.py): every exp, true pow and Dawson RESULT inside the
+// reference's mean_cov_model.h is moved one ulp up or down at random (counter-based generator, seed set by
+// ggp_ref_set_ulp_seed; seed 0 = untouched).  pow(x, 2) stays x * x: g++ -O3 folds it to a multiplication in the
+// reference binary, so it is not a libm result there.  The macros below only rename the calls; the header's text is
+// the reference's, included in place.
+#include <cstdint>
+#include "/root/reference/src/Faddeeva.hh"
+static uint64_t g_ulp_seed = 0, g_ulp_counter = 0;
+static inline double ulp_nudge(double v) {
+    if (g_ulp_seed == 0 || !(v == v) || v == 0.0 || std::isinf(v)) return v;
+    uint64_t z = g_ulp_seed + 0x9e3779b97f4a7c15ull * ++g_ulp_counter;   // splitmix64
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    z ^= z >> 31;
+    return std::nextafter(v, (z & 1) ? HUGE_VAL : -HUGE_VAL);
+}
+static inline double ulp_exp(double x) { return ulp_nudge(std::exp(x)); }
+static inline double ulp_pow(double x, double y) { return y == 2.0 ? x * x : ulp_nudge(std::pow(x, y)); }
+namespace FaddeevaUlp {
+static inline double Dawson(double x) { return ulp_nudge(Faddeeva::Dawson(x)); }
+}
+extern "C" void ggp_ref_set_ulp_seed(unsigned long long seed) { g_ulp_seed = seed; g_ulp_counter = 0; }
+#define exp ulp_exp
+#define pow ulp_pow
+#define Faddeeva FaddeevaUlp
 #include "/root/reference/src/mean_cov_model.h"
+#undef exp
+#undef pow
+#undef Faddeeva
+#else
+#include "/root/reference/src/mean_cov_model.h"
+#endif
 
 extern "C" {
 

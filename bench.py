@@ -10,10 +10,22 @@ log-likelihood is all-reduced every step (NCCL).  Inputs (353 MB/GPU) are larger
   python bench.py [--gpus N] [--steps K] [--warmup W]          our arm (CUDA kernels through the C ABI)
   python bench.py --impl reference ...                         the reference's CPU math on the host cores
 
-One JSON line on stdout (rank 0).  `value` = cell-timepoints/s of the whole job with inputs resident in HBM,
-`e2e` = the same through the host-buffer C-ABI call (pinned host series uploaded and the result read back
-inside the timed region), `roofline` = FP64-pipe fraction of the likelihood kernel, `cpu_baseline` = the
-oracle on one host core on a bounded sample.
+One JSON line on stdout (rank 0).
+  value / ms_per_step   cell-timepoints/s of the whole job with the forest resident in HBM, in the library's FAST likelihood
+                        mode (quadrature + FMA; its gate |dloglik| / |loglik| <= 1e-10 against the reference is evaluated in
+                        this run, `parity`, and the headline falls back to the strict mode if it is not met)
+  strict                the same with the STRICT kernels (bit-identical to the reference's arithmetic)
+  e2e                   through the host-buffer C-ABI call: this step's measurements (log_length, fp; the time grid of an
+                        unchanged genealogy does not travel again) uploaded from pinned host memory + ggp_loglik (host
+                        parameters in, host result out), wall clock
+  e2e_resident          ggp_loglik(host parameters -> host result) on the resident forest: what -m / -s do per evaluation
+  roofline              FP64-pipe fraction of the headline kernel (F_alg = 3 700 flop per cell-timepoint, SURVEY.md 8d, against
+                        the DFMA peak measured in this process); roofline_strict the same for the strict kernel
+  parity                GPU (strict and fast) against the CPU baseline's own result on the SAME trees
+  cpu_baseline          the reference's math on one host core (warm-up + median of 5)
+  configs               BASELINE configs[2..4] on this GPU (short runs): -p on a 1 M-cell forest, a 256-vector slice of the
+                        4096-vector scan, -j on a 100 k-cell forest with two segments
+  strong                (N > 1) ONE 10 000-tree forest partitioned over the ranks: strong scaling of the same evaluation
 """
 import argparse
 import json
@@ -29,11 +41,14 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 F_ALG = 3700.0        # algorithmic FP64 flop per cell-timepoint per directional pass
+F_ALG_PREDICT = 8900.0   # -p: 2 F_alg + 1 500 (combine)
+F_ALG_JOINT = 5500.0     # -j: per emitted joint
 B_ALG = 28.0          # algorithmic bytes per cell-timepoint: time, x, g (f64) + segment (i32)
-# dram__bytes_read.sum + dram__bytes_write.sum of the likelihood kernel per cell-timepoint, from the ncu --set full capture
-# of the largest generation's launch (profiles/r01_s5_loglik_coop_gen5.txt, 6 399 691 ctp)
-DRAM_BYTES_PER_CTP_NCU = (204.285440e6 + 4.971776e6) / 6399691.0
+# dram__bytes_read.sum + dram__bytes_write.sum per cell-timepoint from the ncu --set full captures of the largest
+# generation's launch (6 399 691 ctp): strict profiles/r01_s5_loglik_coop_gen5.txt, fast profiles/r02_fast6_gen5.txt
+DRAM_BYTES_PER_CTP_NCU = {"strict": (204.285440e6 + 4.971776e6) / 6399691.0, "fast": (144.504064e6 + 3.952896e6) / 6399691.0}
 METRIC = "cell-timepoints/s, FP64 log-likelihood evaluation (loglik evals/s in config)"
+GATE = 1e-10          # north star: log-likelihood within relative 1e-10 of the reference
 
 
 def parse():
@@ -44,16 +59,21 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--trees", type=int, default=10000)
     ap.add_argument("--generations", type=int, default=6)
-    ap.add_argument("--cpu-sample-trees", type=int, default=1500)
+    ap.add_argument("--cpu-sample-trees", type=int, default=600)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the configs[2..4] extras")
+    ap.add_argument("--mode", default="auto", choices=["auto", "fast", "strict"], help="headline kernel (auto: fast if its gate is met)")
     return ap.parse_args()
 
 
-def workload_config(args, world):
-    return {"workload": "configs[1]: synthetic forest %d trees x %d generations x ~20 pts/cell per GPU, single "
-                        "log-likelihood eval, gauss division, const noise, fresh mode" % (args.trees, args.generations),
-            "trees_per_gpu": args.trees, "generations": args.generations, "n_vec": 1, "parallelism": "trees sharded x%d" % world,
-            "l2": "inputs (28 B/ctp, ~353 MB per GPU) larger than the 126 MB L2"}
+def workload_config(args, world, extra=None):
+    c = {"workload": "configs[1]: synthetic forest %d trees x %d generations x ~20 pts/cell per GPU, single "
+                     "log-likelihood eval, gauss division, const noise, fresh mode" % (args.trees, args.generations),
+         "trees_per_gpu": args.trees, "generations": args.generations, "n_vec": 1, "parallelism": "trees sharded x%d" % world,
+         "l2": "inputs (28 B/ctp, ~353 MB per GPU) larger than the 126 MB L2"}
+    if extra:
+        c.update(extra)
+    return c
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -141,18 +161,21 @@ def run_reference(args):
     use_ref = oracle_py.use_reference_math(True)
     oracle_py.use_reference_math(False)
     cores = min(host_cores(), 64)
-    trees_per_proc = 120          # ~150 k ctp, ~1 s per process per step
+    trees_per_proc = 120          # ~150 k ctp, ~0.5 s per process per step
     data = ggp.simulate_forest(cores * trees_per_proc, args.generations, seed=20261018)
-    steps, warmup = min(args.steps, 20), min(args.warmup, 3)   # ~1 s per step on the sample below
+    steps, warmup = min(args.steps, 20), args.warmup   # the same warm-up count as the GPU arm; a step is a bounded sample
     v, ctp, ll, t = cpu_pool_bench(data, ggp.PARAMS_CONST_GAUSS, cores, trees_per_proc, steps, warmup, use_ref)
     kind = "reference" if use_ref else "port"
     sample = ("%d trees x %d generations (%d ctp) of the configs[1] forest per step, %d processes x %d trees; %s"
               % (cores * trees_per_proc, args.generations, ctp, cores, trees_per_proc,
-                 "reference mean_cov_model.h + Faddeeva.cc compiled unmodified (oracle/_ref), filter loop = oracle restatement "
-                 "(Eigen is not installable here)" if use_ref else "oracle port (oracle/ggp_oracle.cpp)"))
+                 "reference mean_cov_model.h + Faddeeva.cc compiled unmodified (oracle/_ref) inside the oracle's filter loop, which "
+                 "equals the reference's own likelihood.h / predictions.h bit for bit (tests/test_ref_wrappers.py)" if use_ref
+                 else "oracle port (oracle/ggp_oracle.cpp)"))
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "ctp/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
             "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": workload_config(args, world),
+            "data": "synthetic",
+            "config": workload_config(args, world, {"reference_sample_trees_per_process": trees_per_proc, "reference_processes": cores,
+                                                    "reference_sample_ctp_per_step": int(ctp)}),
             "cpu_baseline": {"value": v, "unit": "ctp/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": "ctp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "loglik_evals_per_s_full_forest": v / (args.trees * (2 ** args.generations - 1) * 20.0), "gpu_launches": 0}
@@ -206,11 +229,30 @@ class ClockSampler:
         return out
 
 
+def global_init_stats(data, world, torch, dist):
+    """population statistics over ALL ranks' cells (moma_input.h:675-735): all-reduce of counts and sums"""
+    n = np.diff(data.cell_offset)
+    sel = n > 1
+    sums = []
+    for idx in (data.cell_offset[:-1][sel], data.cell_offset[1:][sel] - 1):
+        x, g = data.log_length[idx], data.fp[idx]
+        sums += [float(len(idx)), x.sum(), g.sum(), (x * x).sum(), (g * g).sum()]
+    st = torch.tensor(sums, dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(st)
+    st = st.cpu().numpy()
+    out = []
+    for k in (0, 5):
+        c, sx, sg, sxx, sgg = st[k:k + 5]
+        out.append(np.array([sx / c, sg / c, sxx / c - (sx / c) ** 2, sgg / c - (sg / c) ** 2]))
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     import gfp_gaussian_process_b200 as ggp
-    from gfp_gaussian_process_b200 import _lib
+    from gfp_gaussian_process_b200 import _lib, sharding
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -226,23 +268,10 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = _lib.load()
     P = ggp.PARAMS_CONST_GAUSS
+    dp = _lib.c_double_p
 
     data = ggp.simulate_forest(args.trees, args.generations, seed=20261018 + rank)
-    # population statistics over ALL ranks' cells (moma_input.h:675-735): all-reduce of counts and sums
-    n = np.diff(data.cell_offset)
-    sel = n > 1
-    sums = []
-    for idx in (data.cell_offset[:-1][sel], data.cell_offset[1:][sel] - 1):
-        x, g = data.log_length[idx], data.fp[idx]
-        sums += [float(len(idx)), x.sum(), g.sum(), (x * x).sum(), (g * g).sum()]
-    st = torch.tensor(sums, dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(st)
-    st = st.cpu().numpy()
-    for k, name in ((0, "init_f"), (5, "init_r")):
-        c, sx, sg, sxx, sgg = st[k:k + 5]
-        setattr(data, name, np.array([sx / c, sg / c, sxx / c - (sx / c) ** 2, sgg / c - (sg / c) ** 2]))
-
+    data.init_f, data.init_r = global_init_stats(data, world, torch, dist)
     forest = ggp.Forest(data, device=local)
     stream = torch.cuda.current_stream()
     forest.set_stream(stream.cuda_stream)
@@ -251,129 +280,283 @@ def run_ours(args):
     d_out = torch.zeros(1, dtype=torch.float64, device="cuda")
     total = torch.zeros(1, dtype=torch.float64, device="cuda")
 
-    def step():
-        _lib.check(lib.ggp_loglik_device(forest.handle, d_params.data_ptr(), 1, d_out.data_ptr()))
-        total.copy_(d_out)
-        if world > 1:
-            dist.all_reduce(total)
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.3)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kern_ms = 0.0
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    launches = forest.last_launch_count * args.steps
-    if rank == 0:
-        time.sleep(0.2)
-    clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    ll_total = float(total.item())
+    def allmax(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
-    # kernel-only time of the likelihood launches (events inside the library, same stream), separate loop so that the
-    # event sync does not sit in the timed region above
-    for _ in range(args.steps):
-        _lib.check(lib.ggp_loglik_device(forest.handle, d_params.data_ptr(), 1, d_out.data_ptr()))
+    def allsum(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t)
+        return float(t.item())
+
+    ctp_total = allsum(float(n_ctp))
+
+    def timed_resident(fr, steps, warmup, sample_clocks=False):
+        """K steps of (device-resident evaluation + all-reduce of the scalar), CUDA events on the stream, max over ranks"""
+        def step():
+            _lib.check(lib.ggp_loglik_device(fr.handle, d_params.data_ptr(), 1, d_out.data_ptr()))
+            total.copy_(d_out)
+            if world > 1:
+                dist.all_reduce(total)
+        for _ in range(warmup):
+            step()
+        barrier()
+        sampler = ClockSampler(local) if (sample_clocks and rank == 0) else None
+        if sampler:
+            sampler.start()
+            time.sleep(0.3)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = fr.last_launch_count * steps
+        if sampler:
+            time.sleep(0.2)
+        clocks = sampler.stop() if sampler else None
         k = np.zeros(1)
-        _lib.check(lib.ggp_sync_kernel_ms(forest.handle, k.ctypes.data_as(_lib.c_double_p)))
-        kern_ms += float(k[0])
-    kern_ms /= args.steps
+        _lib.check(lib.ggp_sync_kernel_ms(fr.handle, k.ctypes.data_as(dp)))   # also checks the fast mode's validity flags
+        # kernel-only time (events inside the library, same stream), separate loop so that the event sync is outside the timed region
+        kern = []
+        for _ in range(steps):
+            _lib.check(lib.ggp_loglik_device(fr.handle, d_params.data_ptr(), 1, d_out.data_ptr()))
+            _lib.check(lib.ggp_sync_kernel_ms(fr.handle, k.ctypes.data_as(dp)))
+            kern.append(float(k[0]))
+        return allmax(ms) / steps, float(np.mean(kern)), int(launches), float(total.item()), clocks
 
-    # end to end through the host-buffer C-ABI call: pinned host series -> device, host params in, host result out
-    pin = [torch.from_numpy(a).pin_memory() for a in (data.time, data.log_length, data.fp)]
-    torch.cuda.synchronize()
+    # end to end through the host-buffer C-ABI calls
+    pin = [torch.from_numpy(a).pin_memory() for a in (data.log_length, data.fp)]
 
-    def e2e_step():
-        forest.upload_series(pin[0].data_ptr(), pin[1].data_ptr(), pin[2].data_ptr())
-        return ggp.total_likelihood(P, forest)
+    def timed_e2e(fr, steps, upload):
+        def step():
+            if upload:   # this step's measurements; the time grid of the unchanged genealogy stays; statistics travel with the data
+                fr.upload_series(None, pin[0].data_ptr(), pin[1].data_ptr(), data.init_f, data.init_r)
+            return ggp.total_likelihood(P, fr)
+        for _ in range(2):
+            ll = step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            ll = step()
+        torch.cuda.synchronize()
+        return allmax((time.perf_counter() - t0) / steps), allsum(ll)
 
-    for _ in range(2):
-        ll_e2e = e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        ll_e2e = e2e_step()
-    torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - t0) / args.steps
-    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    lle = torch.tensor([ll_e2e], dtype=torch.float64, device="cuda")
-    ctp_all = torch.tensor([float(n_ctp)], dtype=torch.float64, device="cuda")
+    res = {}
+    for mode in ("strict", "fast"):
+        forest.set_mode(mode)
+        ms_step, kern_ms, launches, ll, clocks = timed_resident(forest, args.steps, args.warmup, sample_clocks=True)
+        e2e_s, ll_e2e = timed_e2e(forest, args.steps, True)
+        res_s, _ = timed_e2e(forest, args.steps, False)
+        res[mode] = dict(ms_step=ms_step, kern_ms=kern_ms, launches=launches, loglik=ll, clocks=clocks, e2e_s=e2e_s, loglik_e2e=ll_e2e,
+                         resident_s=res_s, reruns=int(forest.last_strict_reruns))
+    gate_full = abs(res["fast"]["loglik"] - res["strict"]["loglik"]) / abs(res["strict"]["loglik"])
+
+    # strong scaling: ONE forest (the rank-0 seed) partitioned over the ranks by tree, statistics of the whole forest
+    strong = None
     if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        dist.all_reduce(lle)
-        dist.all_reduce(ctp_all)
-    e2e_s = float(te.item())
-    ctp_total = float(ctp_all.item())
+        whole = ggp.simulate_forest(args.trees, args.generations, seed=20261018)
+        whole.init_f, whole.init_r = whole.init_stats()
+        sub, _, _ = sharding.shard(whole, rank, world)
+        fs = ggp.Forest(sub, device=local)
+        fs.set_stream(stream.cuda_stream)
+        strong = {}
+        for mode in ("strict", "fast"):
+            fs.set_mode(mode)
+            ms_s, kern_s, _, ll_s, _ = timed_resident(fs, args.steps, args.warmup)
+            strong[mode] = {"ms_per_step": ms_s, "value": whole.n_ctp / (ms_s * 1e-3), "kernel_ms_max_rank": allmax(kern_s), "loglik": ll_s}
+        strong["ctp_total"] = int(whole.n_ctp)
+        strong["imbalance_max_over_mean_ctp"] = allmax(float(sub.n_ctp)) / (whole.n_ctp / world)
+        strong["what"] = ("one %d-tree forest (seed of rank 0) partitioned over %d ranks by greedy bin packing of trees "
+                          "(sharding.partition_roots), scalar all-reduce per step; value = ctp of the whole forest / max-over-ranks time"
+                          % (args.trees, world))
+        fs.close()
 
     if rank == 0:
         peak = np.zeros(1)
-        _lib.check(lib.ggp_fp64_peak(local, peak.ctypes.data_as(_lib.c_double_p)))
+        _lib.check(lib.ggp_fp64_peak(local, peak.ctypes.data_as(dp)))
         fp64_peak = float(peak[0])
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
             hbm_peak, hbm_src = float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json"
         except Exception:
             hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
-        ms_step = ms / args.steps
-        achieved_tf = n_ctp * F_ALG / (kern_ms * 1e-3) / 1e12
-        line = {
-            "metric": METRIC, "value": ctp_total / (ms_step * 1e-3), "unit": "ctp/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
-            "loglik_evals_per_s": 1e3 / ms_step, "loglik": ll_total, "loglik_e2e": float(lle.item()),
-            "ctp_total": ctp_total, "cells_per_gpu": forest.n_cells,
-            "clocks": clocks,
-            "e2e": {"value": ctp_total / e2e_s, "unit": "ctp/s", "h2d_bytes_per_step": int(3 * 8 * n_ctp + 88),
-                    "d2h_bytes_per_step": 16, "ms_per_step": e2e_s * 1e3,
-                    "what": "ggp_forest_upload_series (time, log_length, fp from pinned host memory) + ggp_loglik (host params in, "
-                            "host log-likelihood and NaN record out), wall clock around the host calls"},
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak,
-                         "traffic": DRAM_BYTES_PER_CTP_NCU * n_ctp, "traffic_unit": "bytes per step (sum over the step's launches; ncu bytes/ctp of "
-                                                                                    "the largest launch x ctp per step)",
-                         "kernel": "ggp_loglik_coop_kernel (%d launches/step, one per generation)" % forest.n_generations,
-                         "kernel_ms_per_step": kern_ms, "flop_per_ctp": F_ALG,
-                         "peak_source": "DFMA micro-benchmark run in this process (ggp_fp64_peak); MEASURED_PEAKS.json holds no FP64 figure",
-                         "hbm": {"achieved": n_ctp * B_ALG / (kern_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                                 "frac": n_ctp * B_ALG / (kern_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src}},
-        }
+
+        def roofline(mode):
+            r = res[mode]
+            ach = n_ctp * F_ALG / (r["kern_ms"] * 1e-3) / 1e12
+            kernel = ("ggp_fast_loglik_kernel<6, 2> (one thread per cell; %d launches per step)" if mode == "fast" else
+                      "ggp_loglik_coop_kernel (four warps per 32 cells; %d launches per step)") % (r["launches"] // args.steps)
+            return {"bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak,
+                    "traffic": DRAM_BYTES_PER_CTP_NCU[mode] * n_ctp,
+                    "traffic_unit": "bytes per step (ncu dram bytes per ctp of the largest launch x ctp per step)",
+                    "kernel": kernel, "kernel_ms_per_step": r["kern_ms"], "flop_per_ctp": F_ALG,
+                    "peak_source": "DFMA micro-benchmark run in this process (ggp_fp64_peak); MEASURED_PEAKS.json holds no FP64 figure",
+                    "note": ("F_alg counts the reference's formulas (38 integrals via Dawson, 26 exp, 3 pow per step); the fast kernel "
+                             "evaluates the same moments with 20 exponentials and no Dawson / pow: ~790 executed FP64 instructions "
+                             "per ctp (ncu), i.e. the fraction is algorithmic work per second over the DFMA peak, not pipe utilisation "
+                             "(FP64 pipe busy 60 %, profiles/r02_fast6_gen5.txt)") if mode == "fast" else
+                            ("strict arithmetic cannot fuse (FMA off) and evaluates 66 exp + 14 Dawson + 3 pow per step bit for bit: "
+                             "3 220 executed FP64 instructions per ctp, FP64 pipe busy 44.5 % (profiles/r01_s5_loglik_coop_gen5.txt)"),
+                    "hbm": {"achieved": n_ctp * B_ALG / (r["kern_ms"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                            "frac": n_ctp * B_ALG / (r["kern_ms"] * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src}}
+
+        def e2e(mode):
+            r = res[mode]
+            return {"value": ctp_total / r["e2e_s"], "unit": "ctp/s", "h2d_bytes_per_step": int(2 * 8 * n_ctp + 88 + 64),
+                    "d2h_bytes_per_step": 16, "ms_per_step": r["e2e_s"] * 1e3,
+                    "what": "ggp_forest_upload_series (this step's log_length and fp from pinned host memory with their init_cells "
+                            "statistics; the unchanged time grid is not sent again) + ggp_loglik (host params in, host log-likelihood "
+                            "and NaN record out), wall clock around the host calls"}
+
+        line = {"metric": METRIC, "unit": "ctp/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "ctp_total": ctp_total, "cells_per_gpu": forest.n_cells}
+
+        parity = {"gate": GATE, "fast_vs_strict_full_forest": gate_full}
         if not args.no_cpu_baseline and world == 1:
             from oracle import oracle_py
             use_ref = oracle_py.use_reference_math(True)
-            sub, _, _ = data.subset(data.roots()[:args.cpu_sample_trees])
+            sub, cells, _ = data.subset(data.roots()[:args.cpu_sample_trees])
             sub.init_f, sub.init_r = data.init_f, data.init_r
             o = oracle_py.Oracle(sub)
-            t0 = time.perf_counter()
-            ll_cpu = o.total_loglik(P)
-            dt = time.perf_counter() - t0
+            ts = []
+            for it in range(6):   # one warm-up + median of 5
+                t0 = time.perf_counter()
+                ll_cpu, pc_cpu = o.total_loglik(P, per_cell=True)
+                if it:
+                    ts.append(time.perf_counter() - t0)
+            dt = float(np.median(ts))
             line["cpu_baseline"] = {"value": sub.n_ctp / dt, "unit": "ctp/s", "cores": 1, "kind": "reference" if use_ref else "port",
-                                    "sample": "first %d trees (%d ctp) of the same forest, one evaluation, %.1f s; %s" % (
-                                        args.cpu_sample_trees, sub.n_ctp, dt,
-                                        "reference mean_cov_model.h + Faddeeva.cc (oracle/_ref) inside the oracle's filter loop" if use_ref
-                                        else "oracle port"), "loglik": ll_cpu}
+                                    "sample": "first %d trees (%d ctp) of the same forest, one warm-up + median of 5 evaluations (%.2f s "
+                                              "each); %s" % (args.cpu_sample_trees, sub.n_ctp, dt,
+                                                             "reference mean_cov_model.h + Faddeeva.cc (oracle/_ref) inside the oracle's filter loop"
+                                                             if use_ref else "oracle port"), "loglik": ll_cpu}
+            # the GPU on the SAME trees
+            fsub = ggp.Forest(sub, device=local)
+            ll_g, pc_g = ggp.total_likelihood(P, fsub, per_cell=True)
+            fsub.set_mode("fast")
+            ll_f = ggp.total_likelihood(P, fsub)
+            fsub.close()
+            parity.update({"sample": "the cpu_baseline's %d trees" % args.cpu_sample_trees,
+                           "rel_err_loglik": abs(ll_g - ll_cpu) / abs(ll_cpu),
+                           "cells_bit_equal": int(np.sum(pc_g.view(np.uint64) == pc_cpu.view(np.uint64))), "cells": int(sub.n_cells),
+                           "fast_rel_err_loglik": abs(ll_f - ll_cpu) / abs(ll_cpu)})
+        gate_ok = gate_full <= GATE and parity.get("fast_rel_err_loglik", 0.0) <= GATE and res["fast"]["reruns"] == 0
+        head = "strict" if (args.mode == "strict" or (args.mode == "auto" and not gate_ok)) else "fast"
+        parity["fast_gate_met"] = bool(gate_ok)
+        r = res[head]
+        line.update({
+            "value": ctp_total / (r["ms_step"] * 1e-3), "ms_per_step": r["ms_step"],
+            "config": workload_config(args, world, {"mode": "%s likelihood kernels (%s)" % (head, "quadrature + FMA, gate 1e-10 met in this run"
+                                                                                             if head == "fast" else "bit-identical to the reference's arithmetic")}),
+            "loglik_evals_per_s": 1e3 / r["ms_step"], "loglik": r["loglik"], "loglik_e2e": r["loglik_e2e"], "clocks": r["clocks"],
+            "e2e": e2e(head),
+            "e2e_resident": {"value": ctp_total / r["resident_s"], "unit": "ctp/s", "ms_per_step": r["resident_s"] * 1e3,
+                             "h2d_bytes_per_step": 88, "d2h_bytes_per_step": 16,
+                             "what": "ggp_loglik(host params -> host log-likelihood) on the resident forest: one -m / -s evaluation"},
+            "gpu_launches": r["launches"], "roofline": roofline(head), "parity": parity})
+        other = "strict" if head == "fast" else "fast"
+        o_ = res[other]
+        line[other] = {"value": ctp_total / (o_["ms_step"] * 1e-3), "ms_per_step": o_["ms_step"], "loglik": o_["loglik"],
+                       "e2e": e2e(other), "e2e_resident_ms": o_["resident_s"] * 1e3, "gpu_launches": o_["launches"], "clocks": o_["clocks"]}
+        line["roofline_" + other] = roofline(other)
+        if strong:
+            line["strong"] = strong
+        if not args.no_configs and world == 1:
+            forest.close()
+            forest = None
+            torch.cuda.empty_cache()
+            line["configs"] = measure_configs(ggp, _lib, lib, torch, local, fp64_peak)
         sys.stdout.flush()
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
-    forest.close()
+    if forest is not None:
+        forest.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_configs(ggp, _lib, lib, torch, device, fp64_peak):
+    """BASELINE configs[2..4] on this GPU, short runs (tools/measure_configs.py holds the long forms)"""
+    import ctypes as C
+    dp = _lib.c_double_p
+    out = {}
+    # configs[2]: -p on a 1 M-cell forest (one GPU's view; 8 GPUs shard the trees), scaled noise + binomial division
+    data = ggp.simulate_forest(15873, 6, noise_model="scaled", division_model="binomial", seed=20261018)
+    f = ggp.Forest(data, device=device)
+    P = np.ascontiguousarray(ggp.PARAMS_SCALED_BINOMIAL.reshape(1, 11))
+    ms = []
+    for _ in range(4):
+        _lib.check(lib.ggp_predict(f.handle, P.ctypes.data_as(dp), 1, None, None, None))
+        ms.append(f.last_kernel_ms)
+    kms = float(np.median(ms[1:]))
+    pins = {k: torch.empty((data.n_ctp, 14), dtype=torch.float64).pin_memory().numpy() for k in ("forward", "backward", "prediction")}
+    ts = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        ggp.prediction_upper14(f, P, out=pins)
+        ts.append(time.perf_counter() - t0)
+    e2e_s = float(np.min(ts[1:]))
+    out["cfg3_predict"] = {"n_cells": int(data.n_cells), "n_ctp": int(data.n_ctp), "kernel_ms": kms,
+                           "ctp_per_s": data.n_ctp / (kms * 1e-3), "flop_per_ctp": F_ALG_PREDICT,
+                           "frac": data.n_ctp * F_ALG_PREDICT / (kms * 1e-3) / 1e12 / fp64_peak,
+                           "e2e_ms": e2e_s * 1e3, "e2e_ctp_per_s": data.n_ctp / e2e_s, "d2h_bytes": int(3 * 14 * 8 * data.n_ctp),
+                           "what": "forward + backward + combine (strict kernels); e2e = ggp_predict14: host params in, all three outputs "
+                                   "as 14 doubles per time point into pinned host memory"}
+    f.close()
+    del pins
+    # configs[3]: a 256-vector slice of the 4096-vector scan over the configs[1] forest, one ggp_loglik call, fresh mode
+    data = ggp.simulate_forest(10000, 6, seed=20261018)
+    f = ggp.Forest(data, device=device)
+    vecs = np.tile(ggp.PARAMS_CONST_GAUSS, (256, 1))
+    for k in range(256):
+        vecs[k, k % 11] *= 0.8 + 0.4 * (k // 11) / 23.0
+    cfg4 = {"n_vec": 256, "n_ctp": int(data.n_ctp)}
+    for mode in ("strict", "fast"):
+        f.set_mode(mode)
+        ggp.total_likelihood(vecs[:8], f, raise_on_nan=False)
+        t0 = time.perf_counter()
+        ll = ggp.total_likelihood(vecs, f, raise_on_nan=False)
+        dt = time.perf_counter() - t0
+        cfg4[mode] = {"evals_per_s": 256 / dt, "ctp_per_s": 256 * data.n_ctp / dt, "kernel_ms": f.last_kernel_ms,
+                      "frac": 256 * data.n_ctp * F_ALG / (f.last_kernel_ms * 1e-3) / 1e12 / fp64_peak, "finite": int(np.isfinite(ll).sum()),
+                      "strict_reruns": int(f.last_strict_reruns)}
+    out["cfg4_scan_slice"] = cfg4
+    f.close()
+    # configs[4]: -j on a 100 k-cell forest with two segments, tol 1e-10
+    P2 = np.stack([ggp.PARAMS_SCALED_BINOMIAL, ggp.PARAMS_SCALED_BINOMIAL * np.array([1, 1, 1, 2, 1, 1, 1, 1, 1, 1, 1.])])
+    data = ggp.simulate_forest(1587, 6, params=ggp.PARAMS_SCALED_BINOMIAL, noise_model="scaled", division_model="binomial",
+                               seed=20261018, n_segments=2)
+    f = ggp.Forest(data, device=device)
+    ggp.prediction_forward_backward(f, P2, forward=False, backward=False, combined=False)
+    ggp.count_joints(f, P2, 1e-10, 0, 1000)          # per-point preparation (cached on the handle)
+    prep_ms = f.last_kernel_ms
+    n_j, walk = 0, []
+    for _ in range(2):
+        n_j = ggp.count_joints(f, P2, 1e-10)
+        walk.append(f.last_kernel_ms)
+    rows = 100000
+    t0 = time.perf_counter()
+    r, c, m, v = ggp.collect_joint_distributions(f, P2, 1e-10, row_begin=0, row_end=rows)
+    rec_s = time.perf_counter() - t0
+    out["cfg5_joints"] = {"n_cells": int(data.n_cells), "n_ctp": int(data.n_ctp), "joints": int(n_j), "prep_ms": prep_ms,
+                          "walk_ms": float(np.min(walk)), "joints_per_s": n_j / (np.min(walk) * 1e-3), "flop_per_joint": F_ALG_JOINT,
+                          "frac": n_j * F_ALG_JOINT / (np.min(walk) * 1e-3) / 1e12 / fp64_peak,
+                          "records_per_s": len(r) / rec_s, "records": int(len(r)),
+                          "what": "every start point, count only (walk); records_per_s = the first %d start points with their records sorted "
+                                  "on the device and copied to host arrays" % rows}
+    f.close()
+    return out
 
 
 if __name__ == "__main__":

@@ -63,6 +63,7 @@ SIGNATURES = {
     "ggp_loglik_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "ggp_sync_kernel_ms": (C.c_int, [C.c_void_p, c_double_p]),
     "ggp_predict": (C.c_int, [C.c_void_p, c_double_p, C.c_int32, c_double_p, c_double_p, c_double_p]),
+    "ggp_predict14": (C.c_int, [C.c_void_p, c_double_p, C.c_int32, c_double_p, c_double_p, c_double_p]),
     "ggp_backward_cell_state": (C.c_int, [C.c_void_p, c_double_p]),
     "ggp_joints": (C.c_int, [C.c_void_p, c_double_p, C.c_int32, C.c_double, C.c_int64, C.c_int64, C.c_int64, c_int64_p, c_int64_p, c_int64_p, c_double_p]),
     "ggp_last_kernel_ms": (C.c_double, [C.c_void_p]),

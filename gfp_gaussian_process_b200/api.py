@@ -128,6 +128,24 @@ def prediction_forward_backward(forest: Forest, params_vecs, forward=True, backw
     return {k: (a[:, :4], a[:, 4:].reshape(M, 4, 4)) for k, a in bufs.items() if a is not None}
 
 
+def prediction_upper14(forest: Forest, params_vecs, forward=True, backward=True, combined=True, out=None):
+    """the same passes, outputs as [n_ctp][14] = 4 means + upper triangle (xx xg xl xq gg gl gq ll lq qq): the numbers
+    write_predictions_to_file prints (predictions.h:575-578), packed on the device (ggp_predict14).  out: optional dict of
+    preallocated (e.g. pinned) [n_ctp][14] float64 arrays to copy into."""
+    lib = _lib.load()
+    p, _ = _as_params(params_vecs)
+    M = forest.n_ctp
+    bufs = {k: ((out[k] if out and k in out else np.empty((M, 14))) if want else None)
+            for k, want in (("forward", forward), ("backward", backward), ("prediction", combined))}
+
+    def ptr(a):
+        return a.ctypes.data_as(_lib.c_double_p) if a is not None else None
+
+    _lib.check(lib.ggp_predict14(forest.handle, p.ctypes.data_as(_lib.c_double_p), p.shape[0],
+                                 ptr(bufs["forward"]), ptr(bufs["backward"]), ptr(bufs["prediction"])))
+    return {k: a for k, a in bufs.items() if a is not None}
+
+
 def collect_joint_distributions(forest: Forest, params_vecs, tolerance_joint=1e-10, row_begin=0, row_end=None, cap=None):
     """collect_joint_distributions (correlation_tree.h:629-648) as a sparse list instead of the dense CSV.
     prediction_forward_backward must have been run on `forest` with the same params_vecs (the reference's -j

@@ -15,6 +15,7 @@
 #include <cstring>
 #include <numeric>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/ggp_b200.h"
@@ -124,6 +125,15 @@ struct ggp_forest {
     bool legacy_loglik = false;           // GGP_B200_LEGACY_LOGLIK=1: one-thread-per-cell likelihood kernel (A/B measurements)
     int fast_nodes = 0;                   // 0 = strict likelihood (bit-exact, the default); N = fast likelihood with an N-node rule
                                           // (ggp_forest_set_mode / GGP_B200_FAST): not bit-exact, fresh-mode ggp_loglik only
+    int fast_blocks_per_sm = 2;           // register budget variant of the fast kernels (GGP_B200_FAST_OCC: 2, 3, 4; measured on
+                                          // configs[1] with 6 nodes: 1.09 / 1.15 / 1.27 ms - the spills of 3 and 4 cost more than the warps buy)
+    bool fast_chunked = true;             // GGP_B200_FAST_CHUNKED=0: the fast kernels run whole generations on one stream
+    // the forest's distinct time steps and, per time point, the index of the step that arrives there (fast likelihood)
+    std::vector<double> dt_values;
+    bool dt_ok = false;                   // false: more than 65 534 distinct steps, the fast mode is unavailable (strict is used)
+    DevBuf<uint16_t> dt_idx;
+    DevBuf<double> d_dt_values;
+    DevBuf<unsigned char> w_ktab;
     int64_t last_reruns = 0;
     int32_t device_fast_vecs = 0;         // vectors of a fast ggp_loglik_device whose flags ggp_sync_kernel_ms still has to read              // vectors of the last fast ggp_loglik that were re-run on the strict path
     // device
@@ -135,7 +145,7 @@ struct ggp_forest {
     DevBuf<double> w_params, w_state, w_partial, w_out, w_cell_ll, w_carry;
     DevBuf<unsigned long long> w_nan;
     DevBuf<int> w_invalid;
-    DevBuf<double> fwd, bwd, comb, bstate, pred_params, prep, jstack;
+    DevBuf<double> fwd, bwd, comb, bstate, pred_params, prep, jstack, pack;
     DevBuf<int32_t> ctp_slot, jstack_slot;
     bool have_prep = false;
     bool have_pred = false;
@@ -157,6 +167,8 @@ struct ggp_forest {
         F.s_root = s_root.p; F.s_cell = s_cell.p; F.s_dfs0 = s_dfs0.p;
         F.model = model;
         for (int i = 0; i < 4; ++i) { F.init_f[i] = L.init_f[i]; F.init_r[i] = L.init_r[i]; }
+        F.dt_idx = dt_idx.p;
+        F.n_dt = (int32_t)dt_values.size();
         return F;
     }
 };
@@ -166,6 +178,47 @@ namespace {
 int check_handle(const ggp_forest* f) {
     if (!f) return fail(GGP_ERR_BAD_ARG, "null forest handle");
     return GGP_OK;
+}
+
+// table of the distinct time steps of the forest (exact comparison of doubles) and its index per time point; the step that
+// arrives at a cell's first point starts at the mother's last point (predictions.h:28-31)
+cudaError_t build_dt_table(ggp_forest* f, const double* time) {
+    const GgpLayout& L = f->L;
+    std::vector<uint16_t> idx((size_t)L.n_ctp, (uint16_t)0xffff);
+    std::unordered_map<uint64_t, int> seen;
+    f->dt_values.clear();
+    f->dt_ok = true;
+    uint64_t last_bits = ~0ull;
+    int last_i = -1;
+    for (int64_t s = 0; s < L.n_cells && f->dt_ok; ++s) {
+        const int64_t off = L.s_off[s];
+        const int32_t par = L.s_parent[s];
+        for (int64_t t = 0; t < L.s_n[s]; ++t) {
+            const int64_t from = t > 0 ? off + t - 1 : (par >= 0 ? L.s_off[par] + L.s_n[par] - 1 : -1);
+            if (from < 0) continue;
+            const double dt = time[off + t] - time[from];
+            uint64_t bits;
+            std::memcpy(&bits, &dt, 8);
+            if (bits != last_bits) {
+                auto it = seen.find(bits);
+                if (it == seen.end()) {
+                    if (f->dt_values.size() >= 65534) { f->dt_ok = false; break; }
+                    it = seen.emplace(bits, (int)f->dt_values.size()).first;
+                    f->dt_values.push_back(dt);
+                }
+                last_bits = bits;
+                last_i = it->second;
+            }
+            idx[(size_t)(off + t)] = (uint16_t)last_i;
+        }
+    }
+    if (!f->dt_ok) { f->dt_values.clear(); return cudaSuccess; }
+    cudaError_t e = f->dt_idx.ensure(idx.size());
+    if (e == cudaSuccess) e = cudaMemcpy(f->dt_idx.p, idx.data(), idx.size() * sizeof(uint16_t), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = f->d_dt_values.ensure(std::max<size_t>(f->dt_values.size(), 1));
+    if (e == cudaSuccess && !f->dt_values.empty())
+        e = cudaMemcpy(f->d_dt_values.p, f->dt_values.data(), f->dt_values.size() * sizeof(double), cudaMemcpyHostToDevice);
+    return e;
 }
 
 int grid_of(int64_t n) { return (int)((n + GGP_BLOCK - 1) / GGP_BLOCK); }
@@ -287,6 +340,8 @@ int ggp_forest_create(const ggp_forest_desc* d, ggp_forest** out) {
             const int n = atoi(m);
             f->fast_nodes = n == 1 ? GGP_FAST_DEFAULT_NODES : (ggp_fast_supported_nodes(n) ? n : 0);
         }
+        if (const char* m = getenv("GGP_B200_FAST_OCC")) f->fast_blocks_per_sm = std::min(4, std::max(2, atoi(m)));
+        if (const char* m = getenv("GGP_B200_FAST_CHUNKED")) f->fast_chunked = atoi(m) != 0;
     }
 
     cudaStream_t s = nullptr;
@@ -310,6 +365,7 @@ int ggp_forest_create(const ggp_forest_desc* d, ggp_forest** out) {
     if (e == cudaSuccess) e = f->s_cell.upload(L.s_cell, s);
     if (e == cudaSuccess) e = f->ctp_slot.upload(L.ctp_slot, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e == cudaSuccess) e = build_dt_table(f, d->time);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&f->copy_stream, cudaStreamNonBlocking);
     f->chunk_ready.assign(L.n_chunks, nullptr);
     f->timeline = getenv("GGP_B200_TIMELINE") != nullptr;
@@ -348,7 +404,7 @@ void ggp_forest_destroy(ggp_forest* f) {
     cudaSetDevice(f->device);
     cudaDeviceSynchronize();
     for (DevBuf<double>* b : {&f->time, &f->x, &f->g, &f->w_params, &f->w_state, &f->w_partial, &f->w_out, &f->w_cell_ll,
-                              &f->w_carry, &f->fwd, &f->bwd, &f->comb, &f->bstate, &f->pred_params, &f->prep, &f->jstack})
+                              &f->w_carry, &f->fwd, &f->bwd, &f->comb, &f->bstate, &f->pred_params, &f->prep, &f->jstack, &f->pack})
         b->release();
     for (DevBuf<int32_t>* b : {&f->seg, &f->comb_seg, &f->s_n, &f->s_parent, &f->s_d1, &f->s_d2, &f->s_root, &f->s_cell, &f->ctp_slot, &f->jstack_slot})
         b->release();
@@ -356,6 +412,7 @@ void ggp_forest_destroy(ggp_forest* f) {
     f->s_dfs0.release();
     f->w_nan.release();
     f->w_invalid.release();
+    f->dt_idx.release(); f->d_dt_values.release(); f->w_ktab.release();
     for (cudaEvent_t ev : f->chunk_ready) if (ev) cudaEventDestroy(ev);
     if (f->compute_done) cudaEventDestroy(f->compute_done);
     if (f->eval_start) cudaEventDestroy(f->eval_start);
@@ -411,6 +468,10 @@ int ggp_forest_upload_series(ggp_forest* f, const double* time, const double* lo
         }
     }
     GGP_CUDA(cudaSetDevice(f->device));
+    if (time) {   // a new time grid: the table of distinct time steps follows it (host pass; an unchanged grid should be passed as NULL)
+        GGP_CUDA(cudaStreamSynchronize(f->stream));
+        GGP_CUDA(build_dt_table(f, time));
+    }
     // the copies run on their own stream, chunk by chunk, behind whatever the handle's stream still reads; the next
     // likelihood evaluation starts on a chunk's trees as soon as that chunk has landed (enqueue_loglik)
     GGP_CUDA(cudaEventRecord(f->compute_done, f->stream));
@@ -502,9 +563,25 @@ int enqueue_loglik(ggp_forest* f, const double* d_params, int32_t n_vec, double*
             const size_t cnt = (size_t)vc * n_partial;
             ggp_fill64_kernel<<<f->fill_grid(cnt), 256, 0, f->stream>>>(reinterpret_cast<unsigned long long*>(f->w_partial.p), 0ull, cnt);
         }
-        const bool multi = streamed && f->chunk_streams;
+        if (d_invalid) {   // the (parameters, dt)-only constants of this vector chunk
+            const size_t kb = ggp_fast_consts_bytes(f->fast_nodes);
+            GGP_CUDA(f->w_ktab.ensure((size_t)vc * f->dt_values.size() * kb));
+            GgpFwdArgs C{};
+            C.params = d_params;
+            if (!d_params) std::memcpy(C.inline_params, f->h_inline_params, (size_t)n_vec * GGP_NP * sizeof(double));
+            C.v0 = v0;
+            C.v_count = vc;
+            GGP_CUDA(ggp_fast_consts_launch(C, f->d_dt_values.p, (int)f->dt_values.size(), f->w_ktab.p, f->fast_nodes, f->stream));
+            ++f->last_launches;
+        }
+        // per_chunk: the forest's upload chunks (groups of whole trees) are evaluated one after the other, each on a stream of
+        // its own, so that the few-block early generations of one chunk run beside the large late generations of another.
+        // Always behind a streamed upload; for the fast kernels (128-thread blocks, two per SM, no shared-memory footprint:
+        // launches of different streams share the SMs) also on a resident forest.
+        const bool per_chunk = streamed || (d_invalid && K > 1 && f->chunk_streams && f->fast_chunked && chunk >= n_vec);
+        const bool multi = per_chunk && f->chunk_streams;
         if (multi) GGP_CUDA(cudaEventRecord(f->eval_start, f->stream));
-        for (int k = 0; k < (streamed ? K : 1); ++k) {
+        for (int k = 0; k < (per_chunk ? K : 1); ++k) {
             // stream of this chunk's launches: its own (behind everything enqueued on the handle's stream so far), the
             // handle's for the last chunk
             const cudaStream_t ks = (multi && k + 1 < K) ? f->chunk_stream[k] : f->stream;
@@ -514,8 +591,8 @@ int enqueue_loglik(ggp_forest* f, const double* d_params, int32_t n_vec, double*
             for (int g = 0; g < f->n_gen; ++g) {
                 const int64_t* row = f->L.gen_chunk_start.data() + (size_t)g * (K + 1);
                 GgpFwdArgs A{};
-                A.slot0 = (int)(streamed ? row[k] : row[0]);
-                A.n_slots = (int)((streamed ? row[k + 1] : row[K]) - A.slot0);
+                A.slot0 = (int)(per_chunk ? row[k] : row[0]);
+                A.n_slots = (int)((per_chunk ? row[k + 1] : row[K]) - A.slot0);
                 if (A.n_slots == 0) continue;
                 A.params = d_params;
                 if (!d_params) std::memcpy(A.inline_params, f->h_inline_params, (size_t)n_vec * GGP_NP * sizeof(double));
@@ -524,14 +601,14 @@ int enqueue_loglik(ggp_forest* f, const double* d_params, int32_t n_vec, double*
                 A.carry = d_carry;
                 A.state = f->w_state.p;
                 A.partial = f->w_partial.p;
-                A.partial0 = f->gen_partial0[(size_t)g * (K + 1) + (streamed ? k : 0)];
+                A.partial0 = f->gen_partial0[(size_t)g * (K + 1) + (per_chunk ? k : 0)];
                 A.n_partial = n_partial;
                 A.cell_ll = d_cell_ll;
                 A.nan_key = d_nan;
                 A.out_fwd = nullptr;
                 const int gx = grid_of(A.n_slots);
                 if (d_invalid) {
-                    GGP_CUDA(ggp_fast_loglik_launch(F, A, d_invalid, f->fast_nodes, ks));
+                    GGP_CUDA(ggp_fast_loglik_launch(F, A, f->w_ktab.p, d_invalid, f->fast_nodes, f->fast_blocks_per_sm, ks));
                 } else if (g == 0 && d_carry && f->legacy_loglik)
                     ggp_forward_kernel<false, true><<<dim3(gx, 1), GGP_BLOCK, GGP_SMEM_BYTES, ks>>>(F, A);
                 else if (g == 0 && d_carry)
@@ -581,11 +658,12 @@ int ggp_loglik(ggp_forest* f, const double* params, int32_t n_vec, double* root_
     GGP_CUDA(f->w_params.ensure((size_t)n_vec * GGP_NP));
     GGP_CUDA(f->w_out.ensure(n_vec));
     GGP_CUDA(f->w_nan.ensure(n_vec));
-    const bool fast = f->fast_nodes > 0 && !root_carry && !f->legacy_loglik;
+    const bool fast = f->fast_nodes > 0 && !root_carry && !f->legacy_loglik && f->dt_ok;
     f->last_reruns = 0;
     if (fast) {
         GGP_CUDA(f->w_invalid.ensure(n_vec));
-        GGP_CUDA(cudaMemsetAsync(f->w_invalid.p, 0, (size_t)n_vec * sizeof(int), s));
+        GGP_CUDA(f->w_invalid.ensure((size_t)n_vec + 1));   // cleared by a kernel: a memset may queue behind a streamed upload's copies
+        ggp_fill64_kernel<<<f->fill_grid(((size_t)n_vec + 1) / 2), 256, 0, s>>>(reinterpret_cast<unsigned long long*>(f->w_invalid.p), 0ull, ((size_t)n_vec + 1) / 2);
     }
     if (out_cell_ll) GGP_CUDA(f->w_cell_ll.ensure((size_t)n_vec * f->n_cells));
     if (root_carry) {
@@ -684,9 +762,9 @@ int ggp_loglik_device(ggp_forest* f, const double* d_params, int32_t n_vec, doub
     GGP_CUDA(f->w_nan.ensure(n_vec));
     ggp_fill64_kernel<<<f->fill_grid((size_t)n_vec), 256, 0, f->stream>>>(f->w_nan.p, ~0ull, (size_t)n_vec);
     f->last_launches = 0;
-    const bool fast = f->fast_nodes > 0 && !f->legacy_loglik;
+    const bool fast = f->fast_nodes > 0 && !f->legacy_loglik && f->dt_ok;
     if (fast) {   // the flags are checked by ggp_sync_kernel_ms
-        GGP_CUDA(f->w_invalid.ensure(n_vec));
+        GGP_CUDA(f->w_invalid.ensure((size_t)n_vec + 1));
         ggp_fill64_kernel<<<f->fill_grid(((size_t)n_vec + 1) / 2), 256, 0, f->stream>>>(reinterpret_cast<unsigned long long*>(f->w_invalid.p), 0ull, ((size_t)n_vec + 1) / 2);
     }
     f->device_fast_vecs = fast ? n_vec : 0;
@@ -714,8 +792,23 @@ int ggp_sync_kernel_ms(ggp_forest* f, double* ms_out) {
     return GGP_OK;
 }
 
-int ggp_predict(ggp_forest* f, const double* params, int32_t n_seg, double* out_forward, double* out_backward,
-                double* out_combined) {
+}  // extern "C"
+
+namespace {
+
+// [n][20] (4 means + row-major 4x4) -> [n][14] (4 means + upper triangle row-major: xx xg xl xq gg gl gq ll lq qq), the 14
+// numbers per time point the reference's writer prints (predictions.h:541-552, 575-578)
+__global__ void __launch_bounds__(256) ggp_pack14_kernel(int64_t n, const double* __restrict__ in20, double* __restrict__ out14) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n * 14) return;
+    const int64_t k = i / 14;
+    const int e = (int)(i - k * 14);
+    constexpr int src[14] = {0, 1, 2, 3, 4, 5, 6, 7, 9, 10, 11, 14, 15, 19};
+    out14[i] = in20[20 * k + src[e]];
+}
+
+int predict_impl(ggp_forest* f, const double* params, int32_t n_seg, double* out_forward, double* out_backward,
+                 double* out_combined, bool pack14) {
     if (int rc = check_handle(f)) return rc;
     if (!params || n_seg <= 0) return fail(GGP_ERR_BAD_ARG, "bad params/n_seg");
     if (f->max_seg >= n_seg) return fail(GGP_ERR_BAD_ARG, "segment index exceeds the number of parameter sets");
@@ -781,16 +874,46 @@ int ggp_predict(ggp_forest* f, const double* params, int32_t n_seg, double* out_
     ++f->last_launches;
     GGP_CUDA(cudaGetLastError());
     GGP_CUDA(cudaEventRecord(f->ev1, s));
-    const size_t bytes = (size_t)M * 20 * sizeof(double);
-    if (out_forward) GGP_CUDA(cudaMemcpyAsync(out_forward, f->fwd.p, bytes, cudaMemcpyDeviceToHost, s));
-    if (out_backward) GGP_CUDA(cudaMemcpyAsync(out_backward, f->bwd.p, bytes, cudaMemcpyDeviceToHost, s));
-    if (out_combined) GGP_CUDA(cudaMemcpyAsync(out_combined, f->comb.p, bytes, cudaMemcpyDeviceToHost, s));
+    if (pack14) {   // 30 % fewer bytes across PCIe: packed on the device, one staging buffer per output so that the copies overlap
+        const size_t bytes = (size_t)M * 14 * sizeof(double);
+        const double* src[3] = {f->fwd.p, f->bwd.p, f->comb.p};
+        double* dst[3] = {out_forward, out_backward, out_combined};
+        int n_out = 0;
+        for (int o = 0; o < 3; ++o) n_out += dst[o] != nullptr;
+        GGP_CUDA(f->pack.ensure((size_t)M * 14 * std::max(n_out, 1)));
+        int slot = 0;
+        for (int o = 0; o < 3; ++o) {
+            if (!dst[o]) continue;
+            double* stage = f->pack.p + (size_t)M * 14 * slot++;
+            ggp_pack14_kernel<<<(unsigned)((M * 14 + 255) / 256), 256, 0, s>>>(M, src[o], stage);
+            GGP_CUDA(cudaMemcpyAsync(dst[o], stage, bytes, cudaMemcpyDeviceToHost, s));
+        }
+    } else {
+        const size_t bytes = (size_t)M * 20 * sizeof(double);
+        if (out_forward) GGP_CUDA(cudaMemcpyAsync(out_forward, f->fwd.p, bytes, cudaMemcpyDeviceToHost, s));
+        if (out_backward) GGP_CUDA(cudaMemcpyAsync(out_backward, f->bwd.p, bytes, cudaMemcpyDeviceToHost, s));
+        if (out_combined) GGP_CUDA(cudaMemcpyAsync(out_combined, f->comb.p, bytes, cudaMemcpyDeviceToHost, s));
+    }
     GGP_CUDA(cudaStreamSynchronize(s));
     float ms = 0.f;
     GGP_CUDA(cudaEventElapsedTime(&ms, f->ev0, f->ev1));
     f->last_ms = ms;
     f->have_pred = true;
     return GGP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ggp_predict(ggp_forest* f, const double* params, int32_t n_seg, double* out_forward, double* out_backward,
+                double* out_combined) {
+    return predict_impl(f, params, n_seg, out_forward, out_backward, out_combined, false);
+}
+
+int ggp_predict14(ggp_forest* f, const double* params, int32_t n_seg, double* out_forward14, double* out_backward14,
+                  double* out_combined14) {
+    return predict_impl(f, params, n_seg, out_forward14, out_backward14, out_combined14, true);
 }
 
 int ggp_backward_cell_state(ggp_forest* f, double* out_cell_state20) {

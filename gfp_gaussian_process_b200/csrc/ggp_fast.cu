@@ -2,22 +2,58 @@
 // generation, mother -> daughter hand-over through the same SoA state buffer and the same fixed-order reduction as the strict
 // path.  Compiled with FMA contraction ON (-fmad=true); nothing of the strict math is included here.
 //
+// What depends on (parameters, dt) only - exp(-b t), the OU noise terms, the quadrature nodes t xi_j and exp(-+gq t xi_j):
+// 11 + 4 N doubles - is tabulated once per (vector, distinct dt of the forest) by ggp_fast_consts_kernel; the forest stores
+// the table index of every time point (2 bytes per point instead of the 8-byte time stamp).  Tables of up to
+// GGP_FAST_SMEM_DT entries are staged in shared memory, larger ones are read through L1.
+//
 // Build: nvcc -std=c++17 -O3 -fmad=true -gencode arch=compute_100a,code=sm_100a -lineinfo -c
 #include "ggp_fast_api.h"
 #include "ggp_fast.cuh"
 
 #define GGP_FAST_BLOCK 128
+#define GGP_FAST_SMEM_DT 16
 
 template <int N>
-__global__ void __launch_bounds__(GGP_FAST_BLOCK) ggp_fast_loglik_kernel(const GgpDevForest F, const GgpFwdArgs A, int* __restrict__ invalid) {
+__global__ void __launch_bounds__(128) ggp_fast_consts_kernel(const GgpFwdArgs A, const double* __restrict__ dt_values, int n_dt,
+                                                              GgpFastConsts<double, N>* __restrict__ ktab) {
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= n_dt * A.v_count) return;
+    const int v = i / n_dt, d = i - v * n_dt;
+    const double* p = A.params ? A.params + (int64_t)(A.v0 + v) * GGP_NP : A.inline_params + (A.v0 + v) * GGP_NP;
+    GgpFastConsts<double, N> K;
+    ggp_fast_consts(K, dt_values[d], p[0], p[1], p[2], p[3], p[4], p[5], p[6], GgpGLRule<N>());
+    ktab[i] = K;
+}
+
+template <int N>
+struct GgpFastConstsTable {
+    const GgpFastConsts<double, N>* tab;   // this vector's entries
+    const uint16_t* __restrict__ idx;
+    __device__ __forceinline__ const GgpFastConsts<double, N>& at(int64_t k, int64_t) const { return tab[idx[k]]; }
+};
+
+// MB = blocks resident per SM the register allocation is made for (2: ~250 registers, 3: 168, 4: 128; measured)
+template <int N, int MB>
+__global__ void __launch_bounds__(GGP_FAST_BLOCK, MB) ggp_fast_loglik_kernel(const GgpDevForest F, const GgpFwdArgs A,
+                                                                        const GgpFastConsts<double, N>* __restrict__ ktab,
+                                                                        int* __restrict__ invalid) {
     __shared__ double sp[GGP_NP];
     __shared__ double red[GGP_FAST_BLOCK / 32];
+    __shared__ GgpFastConsts<double, N> ks[GGP_FAST_SMEM_DT];
     const int lane_slot = blockIdx.x * GGP_FAST_BLOCK + threadIdx.x;
     const bool active = lane_slot < A.n_slots;
     const int slot = A.slot0 + (active ? lane_slot : 0);
     const int v = blockIdx.y;
     if (threadIdx.x < GGP_NP)
         sp[threadIdx.x] = A.params ? A.params[(int64_t)(A.v0 + v) * GGP_NP + threadIdx.x] : A.inline_params[(A.v0 + v) * GGP_NP + threadIdx.x];
+    const GgpFastConsts<double, N>* kv = ktab + (int64_t)v * F.n_dt;
+    if (F.n_dt <= GGP_FAST_SMEM_DT) {
+        const double* src = reinterpret_cast<const double*>(kv);
+        double* dst = reinterpret_cast<double*>(ks);
+        for (int i = threadIdx.x; i < F.n_dt * (int)(sizeof(GgpFastConsts<double, N>) / sizeof(double)); i += GGP_FAST_BLOCK) dst[i] = src[i];
+        kv = ks;
+    }
     __syncthreads();
     double own = 0.0;
     if (active) {
@@ -31,10 +67,9 @@ __global__ void __launch_bounds__(GGP_FAST_BLOCK) ggp_fast_loglik_kernel(const G
 #pragma unroll
             for (int k = 0; k < 10; ++k) s.c[k] = A.state[(4 + k) * vstride + vbase + parent];
         }
-        GgpFastConsts<double, N> K;
-        K.t = __longlong_as_double(0x7ff8000000000000ll);
+        GgpFastConstsTable<N> kp{kv, F.dt_idx};
         bool valid = true;
-        own = ggp_fast_cell<double, N>(F, slot, sp, s, K, GgpGLRule<N>(), valid);
+        own = ggp_fast_cell<double, N>(F, slot, sp, s, kp, valid);
         if (F.s_d1[slot] >= 0 || F.s_d2[slot] >= 0) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) A.state[k * vstride + vbase + slot] = s.m[k];
@@ -58,15 +93,33 @@ __global__ void __launch_bounds__(GGP_FAST_BLOCK) ggp_fast_loglik_kernel(const G
 
 bool ggp_fast_supported_nodes(int n) { return n == 4 || n == 5 || n == 6 || n == 8 || n == 10; }
 
-cudaError_t ggp_fast_loglik_launch(const GgpDevForest& F, const GgpFwdArgs& A, int* invalid, int n_nodes, cudaStream_t stream) {
+size_t ggp_fast_consts_bytes(int n) { return (size_t)(11 + 4 * n) * sizeof(double); }
+
+#define GGP_FAST_DISPATCH(n_nodes, CALL)                    \
+    switch (n_nodes) {                                      \
+        case 4: { constexpr int NN = 4; CALL; } break;      \
+        case 5: { constexpr int NN = 5; CALL; } break;      \
+        case 6: { constexpr int NN = 6; CALL; } break;      \
+        case 8: { constexpr int NN = 8; CALL; } break;      \
+        case 10: { constexpr int NN = 10; CALL; } break;    \
+        default: return cudaErrorInvalidValue;              \
+    }
+
+cudaError_t ggp_fast_consts_launch(const GgpFwdArgs& A, const double* dt_values, int n_dt, void* ktab, int n_nodes, cudaStream_t stream) {
+    const unsigned grid = (unsigned)((n_dt * A.v_count + 127) / 128);
+    GGP_FAST_DISPATCH(n_nodes, (ggp_fast_consts_kernel<NN><<<grid, 128, 0, stream>>>(A, dt_values, n_dt, static_cast<GgpFastConsts<double, NN>*>(ktab))))
+    return cudaGetLastError();
+}
+
+cudaError_t ggp_fast_loglik_launch(const GgpDevForest& F, const GgpFwdArgs& A, const void* ktab, int* invalid, int n_nodes,
+                                   int blocks_per_sm, cudaStream_t stream) {
     const dim3 grid((unsigned)((A.n_slots + GGP_FAST_BLOCK - 1) / GGP_FAST_BLOCK), (unsigned)A.v_count);
-    switch (n_nodes) {
-        case 4: ggp_fast_loglik_kernel<4><<<grid, GGP_FAST_BLOCK, 0, stream>>>(F, A, invalid); break;
-        case 5: ggp_fast_loglik_kernel<5><<<grid, GGP_FAST_BLOCK, 0, stream>>>(F, A, invalid); break;
-        case 6: ggp_fast_loglik_kernel<6><<<grid, GGP_FAST_BLOCK, 0, stream>>>(F, A, invalid); break;
-        case 8: ggp_fast_loglik_kernel<8><<<grid, GGP_FAST_BLOCK, 0, stream>>>(F, A, invalid); break;
-        case 10: ggp_fast_loglik_kernel<10><<<grid, GGP_FAST_BLOCK, 0, stream>>>(F, A, invalid); break;
-        default: return cudaErrorInvalidValue;
+    if (blocks_per_sm <= 2) {
+        GGP_FAST_DISPATCH(n_nodes, (ggp_fast_loglik_kernel<NN, 2><<<grid, GGP_FAST_BLOCK, 0, stream>>>(F, A, static_cast<const GgpFastConsts<double, NN>*>(ktab), invalid)))
+    } else if (blocks_per_sm == 3) {
+        GGP_FAST_DISPATCH(n_nodes, (ggp_fast_loglik_kernel<NN, 3><<<grid, GGP_FAST_BLOCK, 0, stream>>>(F, A, static_cast<const GgpFastConsts<double, NN>*>(ktab), invalid)))
+    } else {
+        GGP_FAST_DISPATCH(n_nodes, (ggp_fast_loglik_kernel<NN, 4><<<grid, GGP_FAST_BLOCK, 0, stream>>>(F, A, static_cast<const GgpFastConsts<double, NN>*>(ktab), invalid)))
     }
     return cudaGetLastError();
 }

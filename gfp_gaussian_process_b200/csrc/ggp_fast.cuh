@@ -260,9 +260,11 @@ GGP_HD void ggp_fast_divide(GgpFastState<T>& s, T var_dx, T var_dg, bool binomia
 // ---- one cell of the likelihood (sc_likelihood, likelihood.h:36-103), fresh mode ------------------------------------
 // s: in = the mother's end-of-cell posterior (ignored for a root), out = this cell's.  Returns the cell's log-evidence sum;
 // clears `valid` if a step left the quadrature's range or a term is NaN (the caller then re-runs the vector strictly).
-template <class T, int N, class GL>
-GGP_HD T ggp_fast_cell(const GgpDevForest& F, int slot, const T* __restrict__ p, GgpFastState<T>& s, GgpFastConsts<T, N>& K,
-                       const GL& gln, bool& valid) {
+// KP supplies the (parameters, dt)-only constants of the step that ARRIVES at time point k of the forest:
+//   const GgpFastConsts<T, N>& KP::at(int64_t k, int64_t from)
+// (host checks: recomputed when dt changes; device: a table over the forest's distinct dt values, ggp_fast.cu).
+template <class T, int N, class KP>
+GGP_HD T ggp_fast_cell(const GgpDevForest& F, int slot, const T* __restrict__ p, GgpFastState<T>& s, KP& kp, bool& valid) {
     const int64_t off = F.s_off[slot];
     const int n = F.s_n[slot];
     const int parent = F.s_parent[slot];
@@ -288,15 +290,33 @@ GGP_HD T ggp_fast_cell(const GgpDevForest& F, int slot, const T* __restrict__ p,
         from = F.s_off[parent] + F.s_n[parent] - 1;
     }
     while (t + 1 < n) {
-        const T dt = T(F.time[off + t + 1]) - T(F.time[from]);
-        if (!(dt == K.t)) ggp_fast_consts(K, dt, p[0], p[1], p[2], p[3], p[4], p[5], p[6], gln);
+        const int64_t k = off + t + 1;
+        const T xk = T(F.x[k]), gk = T(F.g[k]);   // issued before the step's arithmetic
+        const GgpFastConsts<T, N>& K = kp.at(k, from);
         if (!ggp_fast_propagate(s, K, p[0], p[1], p[3], p[4], p[5], p[6], lmax)) valid = false;
         if (t < 0) ggp_fast_divide(s, p[9], p[10], binomial);
         ++t;
-        from = off + t;
-        const T ll = ggp_fast_update(s, T(F.x[from]), T(F.g[from]), p[7], p[8], scaled, fp_auto);
+        from = k;
+        const T ll = ggp_fast_update(s, xk, gk, p[7], p[8], scaled, fp_auto);
         own += ll;
         if (ll != ll) valid = false;
     }
     return own;
 }
+
+// constants recomputed whenever dt changes (host checks, any scalar type)
+template <class T, int N, class GL>
+struct GgpFastConstsOnDemand {
+    const GgpDevForest& F;
+    const T* p;
+    const GL& gln;
+    GgpFastConsts<T, N> K;
+    bool have = false;
+    GgpFastConstsOnDemand(const GgpDevForest& F_, const T* p_, const GL& g_) : F(F_), p(p_), gln(g_) {}
+    const GgpFastConsts<T, N>& at(int64_t k, int64_t from) {
+        const T dt = T(F.time[k]) - T(F.time[from]);
+        if (!have || !(dt == K.t)) ggp_fast_consts(K, dt, p[0], p[1], p[2], p[3], p[4], p[5], p[6], gln);
+        have = true;
+        return K;
+    }
+};

@@ -42,6 +42,10 @@ struct GgpDevForest {
     const int64_t* s_dfs0;    // rank of the cell's first ctp in the reference's depth-first order
     GgpModel model;
     double init_f[4], init_r[4];
+    // fast likelihood only: index into the forest's table of distinct time steps, per time point = the step that arrives
+    // there (from the previous point of the cell, or from the mother's last point); 0xffff at a root's first point
+    const uint16_t* dt_idx;
+    int32_t n_dt;
 };
 
 struct GgpFwdArgs {

@@ -138,6 +138,11 @@ int ggp_loglik_device(ggp_forest* f, const double* d_params, int32_t n_vec, doub
 int ggp_predict(ggp_forest* f, const double* params, int32_t n_seg,
                 double* out_forward, double* out_backward, double* out_combined);
 
+/* the same passes with the outputs in the layout the reference's writer prints (predictions.h:575-578): [n_ctp][14] = 4 means +
+ * the upper triangle row-major (xx xg xl xq gg gl gq ll lq qq), packed on the device: 30 % fewer bytes to the host */
+int ggp_predict14(ggp_forest* f, const double* params, int32_t n_seg,
+                  double* out_forward14, double* out_backward14, double* out_combined14);
+
 /* replaces: collect_joint_distributions (correlation_tree.h:629-648) with a sparse result: record r =
  * (row_ctp[r], col_ctp[r], rec[r][44]): the joint P(z_col, z_row | D) as 8 means (z_col then z_row) and the 36
  * upper-triangular covariances row-major, sorted by (row, col) = the order the reference writes its dense CSV in.

@@ -75,14 +75,13 @@ static int run(const ggp_forest_desc* d, const double* params, int n_vec, double
     for (int v = 0; v < n_vec; ++v) {
         T p[11];
         for (int i = 0; i < 11; ++i) p[i] = (T)params[11 * v + i];
-        GgpFastConsts<T, N> K;
-        K.t = (T)NAN;
+        GgpFastConstsOnDemand<T, N, GL> kp(F, p, gln);
         bool valid = true;
         T total = 0;
         for (int64_t slot = 0; slot < L.n_cells; ++slot) {
             GgpFastState<T> s;
             if (F.s_parent[slot] >= 0) s = state[(size_t)F.s_parent[slot]];
-            const T own = ggp_fast_cell<T, N>(F, (int)slot, p, s, K, gln, valid);
+            const T own = ggp_fast_cell<T, N>(F, (int)slot, p, s, kp, valid);
             state[(size_t)slot] = s;
             if (out_cell_ll) out_cell_ll[(size_t)v * L.n_cells + L.cell_of_slot[slot]] = (double)own;
             total += own;

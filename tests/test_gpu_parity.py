@@ -167,6 +167,24 @@ def test_carry_chain_and_batching():
     f.close()
 
 
+def test_packed_prediction_outputs_are_the_writer_columns():
+    """ggp_predict14: 4 means + upper triangle in the order write_predictions_to_file prints them (predictions.h:575-578),
+    packed on the device; same bits as the corresponding entries of the full outputs"""
+    d = ragged_forest()
+    P = np.stack([ggp.PARAMS_SCALED_BINOMIAL, ggp.PARAMS_SCALED_BINOMIAL * np.array([1, 1, 1, 2, 1, 1, 1, 1, 1, 1, 1.])])
+    f = ggp.Forest(d)
+    full = ggp.prediction_forward_backward(f, P)
+    packed = ggp.prediction_upper14(f, P)
+    iu = [(i, j) for i in range(4) for j in range(i, 4)]
+    for k in ("forward", "backward", "prediction"):
+        assert same_bits(packed[k][:, :4], full[k][0])
+        for c, (i, j) in enumerate(iu):
+            assert same_bits(packed[k][:, 4 + c], full[k][1][:, i, j]), (k, i, j)
+    only = ggp.prediction_upper14(f, P, forward=False, backward=False)
+    assert list(only) == ["prediction"] and same_bits(only["prediction"], packed["prediction"])
+    f.close()
+
+
 def test_segments_ragged_and_single_point_cells():
     d = ragged_forest()
     P = np.stack([ggp.PARAMS_SCALED_BINOMIAL, ggp.PARAMS_SCALED_BINOMIAL * np.array([1, 1, 1, 2, 1, 1, 1, 1, 1, 1, 1.])])

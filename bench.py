@@ -355,11 +355,12 @@ def run_ours(args):
     res = {}
     for mode in ("strict", "fast"):
         forest.set_mode(mode)
+        ggp.total_likelihood(P, forest)   # fast: the library picks the quadrature order from these parameters and the forest's dt
         ms_step, kern_ms, launches, ll, clocks = timed_resident(forest, args.steps, args.warmup, sample_clocks=True)
         e2e_s, ll_e2e = timed_e2e(forest, args.steps, True)
         res_s, _ = timed_e2e(forest, args.steps, False)
         res[mode] = dict(ms_step=ms_step, kern_ms=kern_ms, launches=launches, loglik=ll, clocks=clocks, e2e_s=e2e_s, loglik_e2e=ll_e2e,
-                         resident_s=res_s, reruns=int(forest.last_strict_reruns))
+                         resident_s=res_s, reruns=int(forest.last_strict_reruns), nodes=int(forest.last_fast_nodes))
     gate_full = abs(res["fast"]["loglik"] - res["strict"]["loglik"]) / abs(res["strict"]["loglik"])
 
     # strong scaling: ONE forest (the rank-0 seed) partitioned over the ranks by tree, statistics of the whole forest
@@ -395,17 +396,17 @@ def run_ours(args):
         def roofline(mode):
             r = res[mode]
             ach = n_ctp * F_ALG / (r["kern_ms"] * 1e-3) / 1e12
-            kernel = ("ggp_fast_loglik_kernel<6, 2> (one thread per cell; %d launches per step)" if mode == "fast" else
-                      "ggp_loglik_coop_kernel (four warps per 32 cells; %d launches per step)") % (r["launches"] // args.steps)
+            kernel = (("ggp_fast_loglik_kernel<%d, 3, true> (one thread per cell, %d-node rule; " % (r["nodes"], r["nodes"])) + "%d launches per step)"
+                      if mode == "fast" else "ggp_loglik_coop_kernel (four warps per 32 cells; %d launches per step)") % (r["launches"] // args.steps)
             return {"bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak,
                     "traffic": DRAM_BYTES_PER_CTP_NCU[mode] * n_ctp,
                     "traffic_unit": "bytes per step (ncu dram bytes per ctp of the largest launch x ctp per step)",
                     "kernel": kernel, "kernel_ms_per_step": r["kern_ms"], "flop_per_ctp": F_ALG,
                     "peak_source": "DFMA micro-benchmark run in this process (ggp_fp64_peak); MEASURED_PEAKS.json holds no FP64 figure",
                     "note": ("F_alg counts the reference's formulas (38 integrals via Dawson, 26 exp, 3 pow per step); the fast kernel "
-                             "evaluates the same moments with 20 exponentials and no Dawson / pow: ~790 executed FP64 instructions "
-                             "per ctp (ncu), i.e. the fraction is algorithmic work per second over the DFMA peak, not pipe utilisation "
-                             "(FP64 pipe busy 60 %, profiles/r02_fast6_gen5.txt)") if mode == "fast" else
+                             "evaluates the same moments by quadrature with N + 4 exponentials and no Dawson / pow: ~580 executed FP64 "
+                             "instructions per ctp at 6 nodes (ncu), i.e. the fraction is ALGORITHMIC work per second over the DFMA peak, "
+                             "not pipe utilisation (FP64 pipe busy 54-60 %, profiles/r02_fast6_gen5*.txt)") if mode == "fast" else
                             ("strict arithmetic cannot fuse (FMA off) and evaluates 66 exp + 14 Dawson + 3 pow per step bit for bit: "
                              "3 220 executed FP64 instructions per ctp, FP64 pipe busy 44.5 % (profiles/r01_s5_loglik_coop_gen5.txt)"),
                     "hbm": {"achieved": n_ctp * B_ALG / (r["kern_ms"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
@@ -458,7 +459,7 @@ def run_ours(args):
         r = res[head]
         line.update({
             "value": ctp_total / (r["ms_step"] * 1e-3), "ms_per_step": r["ms_step"],
-            "config": workload_config(args, world, {"mode": "%s likelihood kernels (%s)" % (head, "quadrature + FMA, gate 1e-10 met in this run"
+            "config": workload_config(args, world, {"mode": "%s likelihood kernels (%s)" % (head, ("%d-node quadrature + FMA, gate 1e-10 met in this run" % r["nodes"])
                                                                                              if head == "fast" else "bit-identical to the reference's arithmetic")}),
             "loglik_evals_per_s": 1e3 / r["ms_step"], "loglik": r["loglik"], "loglik_e2e": r["loglik_e2e"], "clocks": r["clocks"],
             "e2e": e2e(head),

@@ -57,6 +57,7 @@ SIGNATURES = {
     "ggp_forest_get_init": (C.c_int, [C.c_void_p, c_double_p, c_double_p]),
     "ggp_forest_set_mode": (C.c_int, [C.c_void_p, C.c_int32]),
     "ggp_forest_get_mode": (C.c_int32, [C.c_void_p]),
+    "ggp_last_fast_nodes": (C.c_int32, [C.c_void_p]),
     "ggp_last_strict_reruns": (C.c_int64, [C.c_void_p]),
     "ggp_init_stats": (C.c_int, [C.POINTER(ForestDesc), c_double_p, c_double_p]),
     "ggp_loglik": (C.c_int, [C.c_void_p, c_double_p, C.c_int32, c_double_p, c_double_p, c_double_p, C.POINTER(NanInfo)]),

@@ -123,10 +123,14 @@ struct ggp_forest {
     int64_t coop_ng4_min_groups = 0;      // launches with at least this many 32-cell groups use 4 groups per block (8 per SM; set at create)
     int coop_variant = 4;                 // GGP_B200_COOP_VARIANT (A/B measurements): 0 = 4 groups/block, block barriers; 2 = 2 groups/block; 3 = 4 groups, per-group barriers
     bool legacy_loglik = false;           // GGP_B200_LEGACY_LOGLIK=1: one-thread-per-cell likelihood kernel (A/B measurements)
-    int fast_nodes = 0;                   // 0 = strict likelihood (bit-exact, the default); N = fast likelihood with an N-node rule
+    int fast_mode = 0;                    // ggp_forest_set_mode: 0 strict (bit-exact, the default), 1 fast with the node count chosen per
+                                          // call from the parameters and the forest's largest time step, N = fast with an N-node rule
+    int fast_nodes = 0;                   // node count of the evaluation being enqueued (0 = strict kernels)
+    int auto_nodes = GGP_FAST_DEFAULT_NODES;   // what mode 1 chose last (ggp_loglik_device, which sees no host parameters, uses it)
+    double dt_max = 0.0;                  // largest time step of the forest
                                           // (ggp_forest_set_mode / GGP_B200_FAST): not bit-exact, fresh-mode ggp_loglik only
-    int fast_blocks_per_sm = 2;           // register budget variant of the fast kernels (GGP_B200_FAST_OCC: 2, 3, 4; measured on
-                                          // configs[1] with 6 nodes: 1.09 / 1.15 / 1.27 ms - the spills of 3 and 4 cost more than the warps buy)
+    int fast_blocks_per_sm = 3;           // register budget variant of the fast kernels (GGP_B200_FAST_OCC: 2, 3, 4 blocks per SM =
+                                          // 242 / 168 / 128 registers; measured on configs[1] with 6 nodes: 0.777 / 0.752 / 0.864 ms)
     bool fast_chunked = true;             // GGP_B200_FAST_CHUNKED=0: the fast kernels run whole generations on one stream
     // the forest's distinct time steps and, per time point, the index of the step that arrives there (fast likelihood)
     std::vector<double> dt_values;
@@ -134,6 +138,7 @@ struct ggp_forest {
     DevBuf<uint16_t> dt_idx;
     DevBuf<double> d_dt_values;
     DevBuf<unsigned char> w_ktab;
+    int forced_nodes = -1;                // >= 0 inside the re-run ladder of ggp_loglik
     int64_t last_reruns = 0;
     int32_t device_fast_vecs = 0;         // vectors of a fast ggp_loglik_device whose flags ggp_sync_kernel_ms still has to read              // vectors of the last fast ggp_loglik that were re-run on the strict path
     // device
@@ -213,6 +218,8 @@ cudaError_t build_dt_table(ggp_forest* f, const double* time) {
         }
     }
     if (!f->dt_ok) { f->dt_values.clear(); return cudaSuccess; }
+    f->dt_max = 0.0;
+    for (double v : f->dt_values) f->dt_max = std::max(f->dt_max, std::fabs(v));
     cudaError_t e = f->dt_idx.ensure(idx.size());
     if (e == cudaSuccess) e = cudaMemcpy(f->dt_idx.p, idx.data(), idx.size() * sizeof(uint16_t), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = f->d_dt_values.ensure(std::max<size_t>(f->dt_values.size(), 1));
@@ -338,7 +345,7 @@ int ggp_forest_create(const ggp_forest_desc* d, ggp_forest** out) {
         if (const char* m = getenv("GGP_B200_STATE_BUDGET")) f->state_budget_bytes = std::max<int64_t>(1, atoll(m));
         if (const char* m = getenv("GGP_B200_FAST")) {   // 1 = the default rule, N = an N-node rule
             const int n = atoi(m);
-            f->fast_nodes = n == 1 ? GGP_FAST_DEFAULT_NODES : (ggp_fast_supported_nodes(n) ? n : 0);
+            f->fast_mode = n == 1 ? 1 : (ggp_fast_supported_nodes(n) ? n : 0);
         }
         if (const char* m = getenv("GGP_B200_FAST_OCC")) f->fast_blocks_per_sm = std::min(4, std::max(2, atoi(m)));
         if (const char* m = getenv("GGP_B200_FAST_CHUNKED")) f->fast_chunked = atoi(m) != 0;
@@ -513,13 +520,12 @@ int ggp_init_stats(const ggp_forest_desc* d, double* init_f4, double* init_r4) {
 
 int ggp_forest_set_mode(ggp_forest* f, int32_t mode) {
     if (int rc = check_handle(f)) return rc;
-    if (mode == GGP_MODE_STRICT) f->fast_nodes = 0;
-    else if (mode == GGP_MODE_FAST) f->fast_nodes = GGP_FAST_DEFAULT_NODES;
-    else if (ggp_fast_supported_nodes(mode)) f->fast_nodes = mode;
+    if (mode == GGP_MODE_STRICT || mode == GGP_MODE_FAST || ggp_fast_supported_nodes(mode)) f->fast_mode = mode;
     else return fail(GGP_ERR_BAD_ARG, "unknown likelihood mode");
     return GGP_OK;
 }
-int32_t ggp_forest_get_mode(const ggp_forest* f) { return f ? f->fast_nodes : -1; }
+int32_t ggp_forest_get_mode(const ggp_forest* f) { return f ? f->fast_mode : -1; }
+int32_t ggp_last_fast_nodes(const ggp_forest* f) { return f ? f->auto_nodes : -1; }
 int64_t ggp_last_strict_reruns(const ggp_forest* f) { return f ? f->last_reruns : -1; }
 
 double ggp_last_kernel_ms(const ggp_forest* f) { return f ? f->last_ms : -1.0; }
@@ -538,6 +544,27 @@ int wait_for_upload(ggp_forest* f) {
 }
 
 // enqueue the likelihood of vectors [0, n_vec) held in d_params; results to d_out [n_vec]
+// node counts of the fast kernels and the largest |d(exponent)/ds| * dt each rule integrates to rounding (GgpFastLmax)
+const int kFastNodes[] = {4, 5, 6, 8, 10};
+const double kFastLmax[] = {0.02, 0.12, 0.5, 1.8, 4.0};
+
+// the smallest rule that covers a parameter vector on this forest: an a-priori bound of |b + lambda + C_xl| + gq + 4 a dt with
+// lambda within three stationary standard deviations of its mean and a <= var_lambda / (4 gamma_lambda), times the largest
+// time step, with a 10 % margin.  The kernels check the actual value at every step; a vector that still leaves the range is
+// re-run with the next rule (then on the strict path).  0 = no rule covers it.
+int pick_fast_nodes(const ggp_forest* f, const double* p) {
+    const double sd_l = std::sqrt(std::fabs(p[2] / (2.0 * p[1])));
+    const double lam = std::fabs(p[6]) + std::fabs(p[0]) + 3.0 * sd_l + std::fabs(p[4]) + std::fabs(p[2] / p[1]) * f->dt_max;
+    const double need = 1.1 * lam * f->dt_max;
+    if (!(need == need)) return 0;
+    for (int i = 0; i < 5; ++i) if (need <= kFastLmax[i]) return kFastNodes[i];
+    return 0;
+}
+int next_fast_nodes(int n) {
+    for (int i = 0; i + 1 < 5; ++i) if (kFastNodes[i] == n) return kFastNodes[i + 1];
+    return 0;
+}
+
 // d_invalid != nullptr: the fast kernels (fresh mode only), which flag the vectors the caller has to re-run strictly
 int enqueue_loglik(ggp_forest* f, const double* d_params, int32_t n_vec, double* d_carry, double* d_out,
                    double* d_cell_ll, unsigned long long* d_nan, int* d_invalid = nullptr) {
@@ -658,8 +685,24 @@ int ggp_loglik(ggp_forest* f, const double* params, int32_t n_vec, double* root_
     GGP_CUDA(f->w_params.ensure((size_t)n_vec * GGP_NP));
     GGP_CUDA(f->w_out.ensure(n_vec));
     GGP_CUDA(f->w_nan.ensure(n_vec));
-    const bool fast = f->fast_nodes > 0 && !root_carry && !f->legacy_loglik && f->dt_ok;
-    f->last_reruns = 0;
+    // node count of this call: forced by the re-run ladder below, the handle's explicit choice, or (mode 1) the smallest rule
+    // that covers every vector of the batch
+    int nodes = 0;
+    if (!root_carry && !f->legacy_loglik && f->dt_ok) {
+        if (f->forced_nodes >= 0) nodes = f->forced_nodes;
+        else if (f->fast_mode > 1) nodes = f->fast_mode;
+        else if (f->fast_mode == 1) {
+            nodes = kFastNodes[0];
+            for (int32_t v = 0; v < n_vec && nodes; ++v) {
+                const int nv = pick_fast_nodes(f, params + (size_t)v * GGP_NP);
+                nodes = nv == 0 ? 0 : std::max(nodes, nv);
+            }
+            if (nodes) f->auto_nodes = nodes;
+        }
+    }
+    f->fast_nodes = nodes;
+    const bool fast = nodes > 0;
+    if (f->forced_nodes < 0) f->last_reruns = 0;
     if (fast) {
         GGP_CUDA(f->w_invalid.ensure(n_vec));
         GGP_CUDA(f->w_invalid.ensure((size_t)n_vec + 1));   // cleared by a kernel: a memset may queue behind a streamed upload's copies
@@ -713,13 +756,16 @@ int ggp_loglik(ggp_forest* f, const double* params, int32_t n_vec, double* root_
             std::vector<double> P(redo.size() * GGP_NP), ll(redo.size()), cl(out_cell_ll ? redo.size() * (size_t)f->n_cells : 0);
             std::vector<ggp_nan_info> ni(redo.size());
             for (size_t i = 0; i < redo.size(); ++i) std::memcpy(&P[i * GGP_NP], params + (size_t)redo[i] * GGP_NP, GGP_NP * sizeof(double));
-            const int keep = f->fast_nodes;
-            f->fast_nodes = 0;
+            // the ladder: the next larger rule, then the strict kernels
+            const int keep = f->forced_nodes;
+            const int64_t reruns_before = f->last_reruns;
+            f->forced_nodes = next_fast_nodes(nodes);
             const int rc = ggp_loglik(f, P.data(), (int32_t)redo.size(), nullptr, ll.data(), out_cell_ll ? cl.data() : nullptr, ni.data());
-            f->fast_nodes = keep;
+            const bool strict_now = f->forced_nodes == 0;
+            f->forced_nodes = keep;
             f->last_ms += ms;
             f->last_launches += launches;
-            f->last_reruns = (int64_t)redo.size();
+            f->last_reruns = strict_now ? reruns_before + (int64_t)redo.size() : f->last_reruns;
             if (rc != GGP_OK && rc != GGP_ERR_NAN) return rc;
             for (int32_t v = 0; v < n_vec; ++v) if (nan) { nan[v].cell = -1; nan[v].t_index = -1; }
             for (size_t i = 0; i < redo.size(); ++i) {
@@ -762,7 +808,8 @@ int ggp_loglik_device(ggp_forest* f, const double* d_params, int32_t n_vec, doub
     GGP_CUDA(f->w_nan.ensure(n_vec));
     ggp_fill64_kernel<<<f->fill_grid((size_t)n_vec), 256, 0, f->stream>>>(f->w_nan.p, ~0ull, (size_t)n_vec);
     f->last_launches = 0;
-    const bool fast = f->fast_nodes > 0 && !f->legacy_loglik && f->dt_ok;
+    f->fast_nodes = (f->legacy_loglik || !f->dt_ok) ? 0 : (f->fast_mode > 1 ? f->fast_mode : (f->fast_mode == 1 ? f->auto_nodes : 0));
+    const bool fast = f->fast_nodes > 0;
     if (fast) {   // the flags are checked by ggp_sync_kernel_ms
         GGP_CUDA(f->w_invalid.ensure((size_t)n_vec + 1));
         ggp_fill64_kernel<<<f->fill_grid(((size_t)n_vec + 1) / 2), 256, 0, f->stream>>>(reinterpret_cast<unsigned long long*>(f->w_invalid.p), 0ull, ((size_t)n_vec + 1) / 2);

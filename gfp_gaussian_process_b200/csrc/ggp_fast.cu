@@ -3,7 +3,7 @@
 // path.  Compiled with FMA contraction ON (-fmad=true); nothing of the strict math is included here.
 //
 // What depends on (parameters, dt) only - exp(-b t), the OU noise terms, the quadrature nodes t xi_j and exp(-+gq t xi_j):
-// 11 + 4 N doubles - is tabulated once per (vector, distinct dt of the forest) by ggp_fast_consts_kernel; the forest stores
+// 16 + 16 N doubles, pre-multiplied for the quadrature sums - is tabulated once per (vector, distinct dt of the forest) by ggp_fast_consts_kernel; the forest stores
 // the table index of every time point (2 bytes per point instead of the 8-byte time stamp).  Tables of up to
 // GGP_FAST_SMEM_DT entries are staged in shared memory, larger ones are read through L1.
 //
@@ -34,13 +34,14 @@ struct GgpFastConstsTable {
 };
 
 // MB = blocks resident per SM the register allocation is made for (2: ~250 registers, 3: 168, 4: 128; measured)
-template <int N, int MB>
+// SMEM: the constants table fits the block's shared copy (n_dt <= GGP_FAST_SMEM_DT): shared-memory loads with known address space
+template <int N, int MB, bool SMEM>
 __global__ void __launch_bounds__(GGP_FAST_BLOCK, MB) ggp_fast_loglik_kernel(const GgpDevForest F, const GgpFwdArgs A,
                                                                         const GgpFastConsts<double, N>* __restrict__ ktab,
                                                                         int* __restrict__ invalid) {
     __shared__ double sp[GGP_NP];
     __shared__ double red[GGP_FAST_BLOCK / 32];
-    __shared__ GgpFastConsts<double, N> ks[GGP_FAST_SMEM_DT];
+    __shared__ GgpFastConsts<double, N> ks[SMEM ? GGP_FAST_SMEM_DT : 1];
     const int lane_slot = blockIdx.x * GGP_FAST_BLOCK + threadIdx.x;
     const bool active = lane_slot < A.n_slots;
     const int slot = A.slot0 + (active ? lane_slot : 0);
@@ -48,11 +49,10 @@ __global__ void __launch_bounds__(GGP_FAST_BLOCK, MB) ggp_fast_loglik_kernel(con
     if (threadIdx.x < GGP_NP)
         sp[threadIdx.x] = A.params ? A.params[(int64_t)(A.v0 + v) * GGP_NP + threadIdx.x] : A.inline_params[(A.v0 + v) * GGP_NP + threadIdx.x];
     const GgpFastConsts<double, N>* kv = ktab + (int64_t)v * F.n_dt;
-    if (F.n_dt <= GGP_FAST_SMEM_DT) {
+    if (SMEM) {
         const double* src = reinterpret_cast<const double*>(kv);
         double* dst = reinterpret_cast<double*>(ks);
         for (int i = threadIdx.x; i < F.n_dt * (int)(sizeof(GgpFastConsts<double, N>) / sizeof(double)); i += GGP_FAST_BLOCK) dst[i] = src[i];
-        kv = ks;
     }
     __syncthreads();
     double own = 0.0;
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(GGP_FAST_BLOCK, MB) ggp_fast_loglik_kernel(con
 #pragma unroll
             for (int k = 0; k < 10; ++k) s.c[k] = A.state[(4 + k) * vstride + vbase + parent];
         }
-        GgpFastConstsTable<N> kp{kv, F.dt_idx};
+        GgpFastConstsTable<N> kp{SMEM ? ks : kv, F.dt_idx};
         bool valid = true;
         own = ggp_fast_cell<double, N>(F, slot, sp, s, kp, valid);
         if (F.s_d1[slot] >= 0 || F.s_d2[slot] >= 0) {
@@ -93,7 +93,6 @@ __global__ void __launch_bounds__(GGP_FAST_BLOCK, MB) ggp_fast_loglik_kernel(con
 
 bool ggp_fast_supported_nodes(int n) { return n == 4 || n == 5 || n == 6 || n == 8 || n == 10; }
 
-size_t ggp_fast_consts_bytes(int n) { return (size_t)(11 + 4 * n) * sizeof(double); }
 
 #define GGP_FAST_DISPATCH(n_nodes, CALL)                    \
     switch (n_nodes) {                                      \
@@ -105,6 +104,17 @@ size_t ggp_fast_consts_bytes(int n) { return (size_t)(11 + 4 * n) * sizeof(doubl
         default: return cudaErrorInvalidValue;              \
     }
 
+size_t ggp_fast_consts_bytes(int n_nodes) {
+    switch (n_nodes) {
+        case 4: return sizeof(GgpFastConsts<double, 4>);
+        case 5: return sizeof(GgpFastConsts<double, 5>);
+        case 6: return sizeof(GgpFastConsts<double, 6>);
+        case 8: return sizeof(GgpFastConsts<double, 8>);
+        case 10: return sizeof(GgpFastConsts<double, 10>);
+    }
+    return 0;
+}
+
 cudaError_t ggp_fast_consts_launch(const GgpFwdArgs& A, const double* dt_values, int n_dt, void* ktab, int n_nodes, cudaStream_t stream) {
     const unsigned grid = (unsigned)((n_dt * A.v_count + 127) / 128);
     GGP_FAST_DISPATCH(n_nodes, (ggp_fast_consts_kernel<NN><<<grid, 128, 0, stream>>>(A, dt_values, n_dt, static_cast<GgpFastConsts<double, NN>*>(ktab))))
@@ -114,12 +124,15 @@ cudaError_t ggp_fast_consts_launch(const GgpFwdArgs& A, const double* dt_values,
 cudaError_t ggp_fast_loglik_launch(const GgpDevForest& F, const GgpFwdArgs& A, const void* ktab, int* invalid, int n_nodes,
                                    int blocks_per_sm, cudaStream_t stream) {
     const dim3 grid((unsigned)((A.n_slots + GGP_FAST_BLOCK - 1) / GGP_FAST_BLOCK), (unsigned)A.v_count);
+    const bool smem = F.n_dt <= GGP_FAST_SMEM_DT;
+#define GGP_FAST_LAUNCH(MBV, SM) GGP_FAST_DISPATCH(n_nodes, (ggp_fast_loglik_kernel<NN, MBV, SM><<<grid, GGP_FAST_BLOCK, 0, stream>>>(F, A, static_cast<const GgpFastConsts<double, NN>*>(ktab), invalid)))
     if (blocks_per_sm <= 2) {
-        GGP_FAST_DISPATCH(n_nodes, (ggp_fast_loglik_kernel<NN, 2><<<grid, GGP_FAST_BLOCK, 0, stream>>>(F, A, static_cast<const GgpFastConsts<double, NN>*>(ktab), invalid)))
+        if (smem) { GGP_FAST_LAUNCH(2, true) } else { GGP_FAST_LAUNCH(2, false) }
     } else if (blocks_per_sm == 3) {
-        GGP_FAST_DISPATCH(n_nodes, (ggp_fast_loglik_kernel<NN, 3><<<grid, GGP_FAST_BLOCK, 0, stream>>>(F, A, static_cast<const GgpFastConsts<double, NN>*>(ktab), invalid)))
+        if (smem) { GGP_FAST_LAUNCH(3, true) } else { GGP_FAST_LAUNCH(3, false) }
     } else {
-        GGP_FAST_DISPATCH(n_nodes, (ggp_fast_loglik_kernel<NN, 4><<<grid, GGP_FAST_BLOCK, 0, stream>>>(F, A, static_cast<const GgpFastConsts<double, NN>*>(ktab), invalid)))
+        if (smem) { GGP_FAST_LAUNCH(4, true) } else { GGP_FAST_LAUNCH(4, false) }
     }
+#undef GGP_FAST_LAUNCH
     return cudaGetLastError();
 }

@@ -70,15 +70,26 @@ struct GgpFastState {
     T c[10];   // covariance, upper triangle row-major: xx xg xl xq gg gl gq ll lq qq
 };
 
-// what depends on the parameters and dt only; recomputed when dt changes
+// what depends on the parameters and dt only (tabulated per distinct dt on the device, recomputed on change on the host).
+// Everything the quadrature sums need is pre-multiplied here, so that a step spends one FMA per (node, moment).
+template <class T>
+struct alignas(16) GgpFastNode {  // one quadrature node, 16 values = 128 bytes: read with 128-bit loads
+    T s, s2;                      // s_j = t xi_j and its square (exponent arguments)
+    T w, ws;                      // weight w_j = t om_j, w_j s_j
+    T wR, wRs, wRs2, wRs3;        // w_j exp(-gq s_j) s_j^k
+    T wSh, wsh;                   // w_j (exp(+gq s_j) - exp(-gq s_j)); w_j (t + s_j)
+    T wRh, wRhs, wRhs2, wRhs3;    // w_j exp(-gq (t + s_j)) (t + s_j)^k
+    T wRph, pad;                  // w_j exp(+gq (t + s_j))
+};
 template <class T, int N>
-struct GgpFastConsts {
+struct alignas(16) GgpFastConsts {
     T t;                          // the dt these were computed for
     T ebt, egl, egq, epgq;        // exp(-b t), exp(-gl t), exp(-gq t), exp(+gq t)
-    T igl, igq, oi;               // 1/gl, 1/gq, (1 - exp(-gl t)) / gl
+    T igq, oi;                    // 1/gq, (1 - exp(-gl t)) / gl
     T kxx, kxl, kll, kqq;         // OU noise contributions to cov_xx, cov_xl, cov_ll, cov_qq
-    T s[N], w[N];                 // nodes t xi_j and weights t om_j
-    T R[N], Rp[N];                // exp(-gq s_j), exp(+gq s_j)
+    T hsq, hsq2;                  // sq2 / (2 gq), sq2 / (2 gq^2)
+    T pad[3];
+    GgpFastNode<T> node[N];
 };
 
 template <class T, int N, class GL>
@@ -90,29 +101,83 @@ GGP_HD void ggp_fast_consts(GgpFastConsts<T, N>& K, T t, T ml, T gl, T sl2, T mq
     K.egl = X::exp_(-gl * t);
     K.egq = X::exp_(-gq * t);
     K.epgq = X::exp_(gq * t);
-    K.igl = T(1) / gl;
+    const T igl = T(1) / gl;
     K.igq = T(1) / gq;
     const T omegl = -X::expm1_(-gl * t);
-    K.oi = omegl * K.igl;
+    K.oi = omegl * igl;
     // mean_cov_model.h:93-95, 117-119, 196-208: the terms without state
-    K.kxx = sl2 * T(0.5) * K.igl * K.igl * K.igl * (T(2) * gl * t + T(4) * X::expm1_(-gl * t) - X::expm1_(T(-2) * gl * t));
+    K.kxx = sl2 * T(0.5) * igl * igl * igl * (T(2) * gl * t + T(4) * X::expm1_(-gl * t) - X::expm1_(T(-2) * gl * t));
     K.kxl = sl2 * T(0.5) * K.oi * K.oi;
-    K.kll = sl2 * T(0.5) * K.igl * (-X::expm1_(T(-2) * gl * t));
+    K.kll = sl2 * T(0.5) * igl * (-X::expm1_(T(-2) * gl * t));
     K.kqq = sq2 * T(0.5) * K.igq * (-X::expm1_(T(-2) * gq * t));
+    K.hsq = sq2 * T(0.5) * K.igq;
+    K.hsq2 = K.hsq * K.igq;
 #pragma unroll
     for (int j = 0; j < N; ++j) {
-        K.s[j] = t * gln.xi(j);
-        K.w[j] = t * gln.om(j);
-        K.R[j] = X::exp_(-gq * K.s[j]);
-        K.Rp[j] = X::exp_(gq * K.s[j]);
+        const T s = t * gln.xi(j), w = t * gln.om(j), sh = t + s;
+        const T R = X::exp_(-gq * s), Rp = X::exp_(gq * s);
+        GgpFastNode<T>& n = K.node[j];
+        n.s = s; n.s2 = s * s;
+        n.w = w; n.ws = w * s;
+        n.wR = w * R; n.wRs = w * R * s; n.wRs2 = w * R * (s * s); n.wRs3 = w * R * (s * s * s);
+        n.wSh = w * (Rp - R);
+        n.wsh = w * sh;
+        const T Rh = R * K.egq;
+        n.wRh = w * Rh; n.wRhs = w * Rh * sh; n.wRhs2 = w * Rh * (sh * sh); n.wRhs3 = w * Rh * (sh * sh * sh);
+        n.wRph = w * (Rp * K.epgq);
+        n.pad = T(0);
     }
+}
+
+// exp(x) for |x| <= 0.01 (degree-6 Taylor polynomial, relative error < 2e-18)
+template <class T>
+GGP_HD T ggp_fast_exp_tiny(T x) {
+    T p = T(1) / T(720);
+    p = p * x + T(1) / T(120);
+    p = p * x + T(1) / T(24);
+    p = p * x + T(1) / T(6);
+    p = p * x + T(0.5);
+    p = p * x + T(1);
+    return p * x + T(1);
+}
+
+// the quadrature sums of one step.  TINY: the two secondary exponents (Cxl s and 2 a t s) stay below 0.01 over the step, their
+// exponentials are polynomials; else the library's exp.  Every sum is one FMA per node against a pre-multiplied constant.
+template <class T, int N, bool TINY>
+GGP_HD void ggp_fast_moments(const GgpFastConsts<T, N>& K, T a, T B0, T Cxl, T EH, T* __restrict__ M) {
+    typedef GgpFx<T> X;
+    const T t = K.t, twoat = T(2) * a * t;
+    T MB0 = 0, MB1 = 0, MBm0 = 0, MBm1 = 0, MBm2 = 0, MBs0 = 0;
+    T MW0 = 0, MW1 = 0, MWm0 = 0, MWm1 = 0, MWm2 = 0, MWm3 = 0;
+    T NW0 = 0, NW1 = 0, NWm0 = 0, NWm1 = 0, NWm2 = 0, NWm3 = 0, NWp0 = 0;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        const GgpFastNode<T> n = K.node[j];
+        const T s = n.s;
+        const T A = X::exp_(a * n.s2 + B0 * s);               // exp(a s^2 + B0 s)
+        const T V = TINY ? ggp_fast_exp_tiny(Cxl * s) : X::exp_(Cxl * s);
+        const T U = TINY ? ggp_fast_exp_tiny(twoat * s) : X::exp_(twoat * s);
+        const T AW = A * V;                                    // exp(a s^2 + W s), W = B0 + Cxl
+        const T H = AW * (U * EH);                             // exp(a s'^2 + W s'), s' = t + s, EH = exp(t (W + a t))
+        MB0 += n.w * A; MB1 += n.ws * A;
+        MBm0 += n.wR * A; MBm1 += n.wRs * A; MBm2 += n.wRs2 * A;
+        MBs0 += n.wSh * A;
+        MW0 += n.w * AW; MW1 += n.ws * AW;
+        MWm0 += n.wR * AW; MWm1 += n.wRs * AW; MWm2 += n.wRs2 * AW; MWm3 += n.wRs3 * AW;
+        NW0 += n.w * H; NW1 += n.wsh * H;
+        NWm0 += n.wRh * H; NWm1 += n.wRhs * H; NWm2 += n.wRhs2 * H; NWm3 += n.wRhs3 * H;
+        NWp0 += n.wRph * H;
+    }
+    M[0] = MB0; M[1] = MB1; M[2] = MBm0; M[3] = MBm1; M[4] = MBm2; M[5] = MBs0;
+    M[6] = MW0; M[7] = MW1; M[8] = MWm0; M[9] = MWm1; M[10] = MWm2; M[11] = MWm3;
+    M[12] = NW0; M[13] = NW1; M[14] = NWm0; M[15] = NWm1; M[16] = NWm2; M[17] = NWm3; M[18] = NWp0;
 }
 
 // one propagation step over K.t; returns false if the step is outside the quadrature's validity range
 template <class T, int N>
 GGP_HD bool ggp_fast_propagate(GgpFastState<T>& st, const GgpFastConsts<T, N>& K, T ml, T gl, T mq, T gq, T sq2, T b, T lmax) {
     typedef GgpFx<T> X;
-    (void)gl;
+    (void)gl; (void)sq2;
     const T bx = st.m[0], bg = st.m[1], bl = st.m[2], bq = st.m[3];
     const T Cxx = st.c[0], Cxg = st.c[1], Cxl = st.c[2], Cxq = st.c[3], Cgg = st.c[4], Cgl = st.c[5], Cgq = st.c[6],
             Cll = st.c[7], Clq = st.c[8], Cqq = st.c[9];
@@ -124,37 +189,20 @@ GGP_HD bool ggp_fast_propagate(GgpFastState<T>& st, const GgpFastConsts<T, N>& K
     const bool ok = (a >= T(0)) && X::finite_(lam) && (lam * t <= lmax);
 
     // ---- the 19 moments of the step: sum_j w_j s_j^k * (exponential), mean_cov_model.h:9-67 by quadrature ----
-    T MB0 = 0, MB1 = 0, MBm0 = 0, MBm1 = 0, MBm2 = 0, MBs0 = 0;         // [0,t]: B0; B0 - gq; (B0 + gq) - (B0 - gq)
-    T MW0 = 0, MW1 = 0, MWm0 = 0, MWm1 = 0, MWm2 = 0, MWm3 = 0;        // [0,t]: W; W - gq
-    T NW0 = 0, NW1 = 0, NWm0 = 0, NWm1 = 0, NWm2 = 0, NWm3 = 0, NWp0 = 0;   // [t,2t]: W; W - gq; W + gq
-#pragma unroll
-    for (int j = 0; j < N; ++j) {
-        const T s = K.s[j], w = K.w[j], sh = t + s;
-        const T A = X::exp_(s * (B0 + a * s));
-        const T AW = X::exp_(s * (W + a * s));
-        const T H = X::exp_(sh * (W + a * sh));
-        const T wa = w * A, war = wa * K.R[j];
-        MB0 += wa; MB1 += wa * s;
-        MBm0 += war; MBm1 += war * s; MBm2 += war * (s * s);
-        MBs0 += wa * (K.Rp[j] - K.R[j]);
-        const T ww = w * AW, wwr = ww * K.R[j];
-        MW0 += ww; MW1 += ww * s;
-        MWm0 += wwr; MWm1 += wwr * s; MWm2 += wwr * (s * s); MWm3 += wwr * (s * s * s);
-        const T wh = w * H, whr = wh * (K.R[j] * K.egq);
-        NW0 += wh; NW1 += wh * sh;
-        NWm0 += whr; NWm1 += whr * sh; NWm2 += whr * (sh * sh); NWm3 += whr * (sh * sh * sh);
-        NWp0 += wh * (K.Rp[j] * K.epgq);
-    }
+    const T EH = X::exp_(t * (W + a * t));
+    T M[19];
+    const T sec = X::abs_(Cxl) > T(2) * a * t ? X::abs_(Cxl) : T(2) * a * t;
+    if (sec * t <= T(0.01)) ggp_fast_moments<T, N, true>(K, a, B0, Cxl, EH, M);
+    else ggp_fast_moments<T, N, false>(K, a, B0, Cxl, EH, M);
     // exp(c): c0 = bx + Cxx/2 - b t (B-family, mean_cov_model.h:76-115), c5 = 2 (bx + Cxx - b t) (W-family, :124-164)
-    const T Ec0 = X::exp_(bx + T(0.5) * Cxx) * K.ebt;
-    const T Ec5 = X::exp_(T(2) * (bx + Cxx)) * (K.ebt * K.ebt);
-    const T JB0 = Ec0 * MB0, JB1 = Ec0 * MB1;                          // I_k(B0, c0; 0, t)
-    const T JBm0 = Ec0 * MBm0, JBm1 = Ec0 * MBm1, JBm2 = Ec0 * MBm2;   // I_k(B0 - gq, c0; 0, t)
-    const T JBs0 = Ec0 * MBs0;                                         // I_0(B0 + gq, c0) - I_0(B0 - gq, c0)
-    const T L0 = Ec5 * MW0, L1 = Ec5 * MW1, Lh0 = Ec5 * NW0, Lh1 = Ec5 * NW1;
-    const T Q0 = Ec5 * MWm0, Q1 = Ec5 * MWm1, Q2 = Ec5 * MWm2, Q3 = Ec5 * MWm3;
-    const T Qh0 = Ec5 * NWm0, Qh1 = Ec5 * NWm1, Qh2 = Ec5 * NWm2, Qh3 = Ec5 * NWm3;
-    const T Ph0 = Ec5 * NWp0;
+    const T E1 = X::exp_(bx + T(0.5) * Cxx);
+    const T Ec0 = E1 * K.ebt;
+    const T Ec5 = (E1 * K.ebt) * (E1 * K.ebt) * X::exp_(Cxx);
+    const T JB0 = Ec0 * M[0], JB1 = Ec0 * M[1];                        // I_k(B0, c0; 0, t)
+    const T JBm0 = Ec0 * M[2], JBm1 = Ec0 * M[3], JBm2 = Ec0 * M[4];   // I_k(B0 - gq, c0; 0, t)
+    const T JBs0 = Ec0 * M[5];                                         // I_0(B0 + gq, c0) - I_0(B0 - gq, c0)
+    const T L0 = M[6], L1 = M[7], Q0 = M[8], Q1 = M[9], Q2 = M[10], Q3 = M[11];          // W-family over [0, t], without exp(c5)
+    const T Lh0 = M[12], Lh1 = M[13], Qh0 = M[14], Qh1 = M[15], Qh2 = M[16], Qh3 = M[17], Ph0 = M[18];   // over [t, 2t]
 
     const T dq = bq + Cxq - mq;
     const T G1 = mq * JB0 + dq * JBm0 + Clq * JBm1;   // mean_g - bg e^{-bt}, mean_cov_model.h:76-80
@@ -175,7 +223,7 @@ GGP_HD bool ggp_fast_propagate(GgpFastState<T>& st, const GgpFastConsts<T, N>& K
     const T n_xq = ga * egq;                                                  // :120-122
     // lambda and q rows
     const T n_gl = egl * (ebt * Cgl + Cxl * G1 + Cll * G2 + Clq * JBm0);      // :166-176, central form
-    const T n_gq = egq * (ebt * Cgq + Cxq * G1 + Clq * G2 + Cqq * JBm0 + sq2 * T(0.5) * igq * JBs0);   // :178-192, central form
+    const T n_gq = egq * (ebt * Cgq + Cxq * G1 + Clq * G2 + Cqq * JBm0 + K.hsq * JBs0);   // :178-192, central form
     const T n_ll = Cll * (egl * egl) + K.kll;                                 // :196-198
     const T n_lq = Clq * egl * egq;                                           // :200-202
     const T n_qq = Cqq * (egq * egq) + K.kqq;                                 // :204-208
@@ -184,16 +232,16 @@ GGP_HD bool ggp_fast_propagate(GgpFastState<T>& st, const GgpFastConsts<T, N>& K
     const T v2 = e2 * e2 + Cqq;
     const T cm = T(2) * Clq * mq * igq;         // 2 Clq mq / gq
     const T me = T(2) * mq * e2 * igq;          // (2 bq mq + 4 Cxq mq - 2 mq^2) / gq
-    const T hs = sq2 * T(0.5) * igq;            // sq2 / (2 gq)
-    const T S2 =
+    const T hs = K.hsq, hs2 = K.hsq2;           // sq2 / (2 gq), sq2 / (2 gq^2)
+    const T S2 = Ec5 * (
         (cm + mq * mq) * L1 + (v2 - cm - hs) * Q1 - (mq * mq + cm * egq) * Lh1
         + (hs - v2 + T(4) * Clq * t * e2 + cm * K.epgq) * Qh1
         + (Clq * Clq) * (Q3 - Qh3)
         + T(2) * Clq * e2 * Q2 + T(2) * Clq * (Clq * t - e2) * Qh2
-        + (me + hs * igq) * L0 - (me + hs * igq) * Q0
-        + (hs * igq + T(2) * mq * mq * t - me * egq) * Lh0
-        + (T(2) * t * v2 - sq2 * t * igq + me * K.epgq) * Qh0
-        - hs * igq * (egq * egq) * Ph0;
+        + (me + hs2) * (L0 - Q0)
+        + (hs2 + T(2) * mq * mq * t - me * egq) * Lh0
+        + (T(2) * t * (v2 - hs) + me * K.epgq) * Qh0
+        - hs2 * (egq * egq) * Ph0);
     const T n_gg = Cgg * (ebt * ebt) + T(2) * ebt * (Cxg * G1 + Cgl * G2 + Cgq * JBm0) + (S2 - G1 * G1);
 
     st.m[0] = nm0; st.m[1] = nm1; st.m[2] = nm2; st.m[3] = nm3;
@@ -202,18 +250,26 @@ GGP_HD bool ggp_fast_propagate(GgpFastState<T>& st, const GgpFastConsts<T, N>& K
     return ok;
 }
 
-// measurement update and log-evidence term (likelihood.h:26-32, 53-69, predictions.h:84-89), symmetric covariance
+// measurement update (predictions.h:84-89) and the log-evidence term of likelihood.h:26-32 in two parts: returns the quadratic
+// form -1/2 r^T S^-1 r and multiplies det S into `pdet`; the caller takes ONE logarithm of the running product per cell
+// (sum of log det = log of the product; the product is folded into `lsum` before it can leave the double range).
 template <class T>
-GGP_HD T ggp_fast_update(GgpFastState<T>& s, T x, T g, T var_x, T var_g, bool noise_scaled, T fp_auto) {
+GGP_HD T ggp_fast_update(GgpFastState<T>& s, T x, T g, T var_x, T var_g, bool noise_scaled, T fp_auto, T& pdet, T& lsum, bool& valid) {
     typedef GgpFx<T> X;
     const T r0 = x - s.m[0], r1 = g - s.m[1];
     const T D11 = noise_scaled ? var_g * (s.m[1] + fp_auto) : var_g;
     const T S00 = s.c[0] + var_x, S01 = s.c[1], S11 = s.c[4] + D11;
     const T det = S00 * S11 - S01 * S01;
+    if (!(det > T(0))) valid = false;   // log of a non-positive determinant: NaN in the reference; the strict path reports it
+    pdet *= det;
+    if (!(pdet < T(1e100) && pdet > T(1e-100))) {
+        lsum += X::log_(pdet);
+        pdet = T(1);
+    }
     const T id = T(1) / det;
     const T Si00 = S11 * id, Si01 = -S01 * id, Si11 = S00 * id;
     const T q0 = Si00 * r0 + Si01 * r1, q1 = Si01 * r0 + Si11 * r1;   // Si r
-    const T ll = T(-0.5) * (r0 * q0 + r1 * q1) - T(0.5) * X::log_(det) - T(3.6757541328186907);   // 2 log(2 pi) as likelihood.h:31 writes it
+    const T qf = T(-0.5) * (r0 * q0 + r1 * q1);
     // K = C[0:2, :]: rows (xx xg xl xq), (xg gg gl gq); T_i = K_i^T Si
     const T K0[4] = {s.c[0], s.c[1], s.c[2], s.c[3]};
     const T K1[4] = {s.c[1], s.c[4], s.c[5], s.c[6]};
@@ -223,8 +279,10 @@ GGP_HD T ggp_fast_update(GgpFastState<T>& s, T x, T g, T var_x, T var_g, bool no
         T0[i] = K0[i] * Si00 + K1[i] * Si01;
         T1[i] = K0[i] * Si01 + K1[i] * Si11;
     }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) s.m[i] += T0[i] * r0 + T1[i] * r1;
+    s.m[0] += K0[0] * q0 + K1[0] * q1;   // m += K^T Si r
+    s.m[1] += K0[1] * q0 + K1[1] * q1;
+    s.m[2] += K0[2] * q0 + K1[2] * q1;
+    s.m[3] += K0[3] * q0 + K1[3] * q1;
     T n[10];
     n[0] = s.c[0] - (T0[0] * K0[0] + T1[0] * K1[0]);
     n[1] = s.c[1] - (T0[0] * K0[1] + T1[0] * K1[1]);
@@ -238,7 +296,7 @@ GGP_HD T ggp_fast_update(GgpFastState<T>& s, T x, T g, T var_x, T var_g, bool no
     n[9] = s.c[9] - (T0[3] * K0[3] + T1[3] * K1[3]);
 #pragma unroll
     for (int i = 0; i < 10; ++i) s.c[i] = n[i];
-    return ll;
+    return qf;
 }
 
 // mother's last posterior, already propagated over the gap -> daughter's prior (predictions.h:18-61)
@@ -270,7 +328,7 @@ GGP_HD T ggp_fast_cell(const GgpDevForest& F, int slot, const T* __restrict__ p,
     const int parent = F.s_parent[slot];
     const bool scaled = F.model.noise_scaled != 0, binomial = F.model.division_binomial != 0;
     const T fp_auto = T(F.model.fp_auto), lmax = T(GgpFastLmax<N>::v());
-    T own = T(0);
+    T own = T(0), pdet = T(1), lsum = T(0);
     int t;
     int64_t from;
     if (parent < 0) {   // init_sc_distribution, predictions.h:63-78 (first evaluation: off-diagonals are zero)
@@ -280,9 +338,7 @@ GGP_HD T ggp_fast_cell(const GgpDevForest& F, int slot, const T* __restrict__ p,
         s.c[0] = T(F.init_f[2]); s.c[4] = T(F.init_f[3]);
         s.c[7] = p[2] / (T(2) * p[1]);
         s.c[9] = p[5] / (T(2) * p[4]);
-        const T ll = ggp_fast_update(s, T(F.x[off]), T(F.g[off]), p[7], p[8], scaled, fp_auto);
-        own += ll;
-        if (ll != ll) valid = false;
+        own += ggp_fast_update(s, T(F.x[off]), T(F.g[off]), p[7], p[8], scaled, fp_auto, pdet, lsum, valid);
         t = 0;
         from = off;
     } else {
@@ -297,10 +353,11 @@ GGP_HD T ggp_fast_cell(const GgpDevForest& F, int slot, const T* __restrict__ p,
         if (t < 0) ggp_fast_divide(s, p[9], p[10], binomial);
         ++t;
         from = k;
-        const T ll = ggp_fast_update(s, xk, gk, p[7], p[8], scaled, fp_auto);
-        own += ll;
-        if (ll != ll) valid = false;
+        own += ggp_fast_update(s, xk, gk, p[7], p[8], scaled, fp_auto, pdet, lsum, valid);
     }
+    // sum over the cell's points of -1/2 log det S - 2 log(2 pi) (the constant as likelihood.h:31 writes it)
+    own = own - T(0.5) * (lsum + GgpFx<T>::log_(pdet)) - T(n) * T(3.6757541328186907);
+    if (own != own) valid = false;
     return own;
 }
 

@@ -201,7 +201,12 @@ class Forest:
     @property
     def mode(self):
         n = self._lib.ggp_forest_get_mode(self._h)
-        return "strict" if n == 0 else f"fast{n}"
+        return "strict" if n == 0 else ("fast" if n == 1 else f"fast{n}")
+
+    @property
+    def last_fast_nodes(self):
+        """quadrature order the fast mode chose for the last ggp_loglik"""
+        return self._lib.ggp_last_fast_nodes(self._h)
 
     @property
     def last_strict_reruns(self):

@@ -41,7 +41,10 @@ enum { GGP_DIVISION_GAUSS = 0, GGP_DIVISION_BINOMIAL = 1 }; /* MOMAdata::cell_di
  *   it differs from the reference by the reference's own rounding noise (|dloglik| / |loglik| <= 1e-10 is the gate,
  *   DESIGN.md).  A parameter vector whose time steps leave the rule's validity range, or that meets a NaN term, is re-run
  *   on the strict path inside ggp_loglik, so NaN reports are always the reference's.
- * A value N in {4, 5, 6, 8, 10} selects the fast mode with an N-node rule (GGP_MODE_FAST = 6 nodes). */
+ * GGP_MODE_FAST picks the smallest rule of {4, 5, 6, 8, 10} nodes that covers the call's parameter vectors on this forest
+ * (an a-priori bound; the kernels check every step, and a vector that still leaves the range climbs to the next rule, then to
+ * the strict path).  A value N in {4, 5, 6, 8, 10} forces the N-node rule.  ggp_loglik_device, which sees no host
+ * parameters, uses the rule the last ggp_loglik chose (6 nodes before any). */
 enum { GGP_MODE_STRICT = 0, GGP_MODE_FAST = 1 };
 
 typedef struct ggp_forest ggp_forest;
@@ -104,7 +107,8 @@ int ggp_forest_get_init(const ggp_forest* f, double* init_f4, double* init_r4);
 /* likelihood arithmetic of this handle: GGP_MODE_STRICT (default), GGP_MODE_FAST, or a node count (see above); also set by
  * the environment variable GGP_B200_FAST at ggp_forest_create */
 int ggp_forest_set_mode(ggp_forest* f, int32_t mode);
-int32_t ggp_forest_get_mode(const ggp_forest* f);   /* 0 = strict, else the fast mode's node count */
+int32_t ggp_forest_get_mode(const ggp_forest* f);   /* the value set: 0 strict, 1 fast, or a forced node count */
+int32_t ggp_last_fast_nodes(const ggp_forest* f);   /* node count GGP_MODE_FAST chose last */
 /* number of parameter vectors of the last fast ggp_loglik that were re-run on the strict path */
 int64_t ggp_last_strict_reruns(const ggp_forest* f);
 /* the init_cells_f / init_cells_r statistics of a data set (moma_input.h:675-735) without creating a forest: what a caller

@@ -28,7 +28,7 @@ def test_fast_gate_on_small_forests(noise, division):
     P = ggp.PARAMS_CONST_GAUSS if noise == "const" else ggp.PARAMS_SCALED_BINOMIAL
     d = ggp.simulate_forest(60, 5, params=P, noise_model=noise, division_model=division, seed=51)
     f = ggp.Forest(d)
-    f.set_mode("fast")
+    f.set_mode(6)
     assert f.mode == "fast6"
     vecs = np.stack([P, P * 1.03, P * 0.96])
     ll, pc = ggp.total_likelihood(vecs, f, per_cell=True)
@@ -41,6 +41,11 @@ def test_fast_gate_on_small_forests(noise, division):
     assert np.max(np.abs(pc - pc_h) / np.abs(pc_h)) <= 1e-11
     # single calls equal the batch, run to run identical
     assert ggp.total_likelihood(vecs[1], f) == ll[1] and same_bits(ggp.total_likelihood(vecs, f), ll)
+    # "fast" picks the rule from the parameters and the forest's time step (5 nodes at dt = 3.5, 6 at dt = 15): same gate
+    f.set_mode("fast")
+    ll_auto = ggp.total_likelihood(vecs, f)
+    assert f.last_fast_nodes == (5 if noise == "const" else 6) and f.last_strict_reruns == 0
+    assert np.max(np.abs(ll_auto - ll) / np.abs(ll)) <= 1e-13
     # back to strict: the bit-exact path again
     f.set_mode("strict")
     assert same_bits(ggp.total_likelihood(P, f, per_cell=True)[1], o.total_loglik(P, per_cell=True)[1])
@@ -65,7 +70,7 @@ def test_fast_gate_at_full_size():
     d = ggp.simulate_forest(10000, 6, seed=20261018)
     f = ggp.Forest(d)
     strict = ggp.total_likelihood(P, f)
-    f.set_mode("fast")
+    f.set_mode(6)
     vecs = np.stack([P, P * 1.02])
     fast = ggp.total_likelihood(vecs, f)
     print(f"configs[1]: fast {fast[0]!r} strict {strict!r} rel {rel(fast[0], strict):.2e}")
@@ -73,7 +78,7 @@ def test_fast_gate_at_full_size():
     sub, cells, ctp = d.subset(d.roots()[100:110])
     host, valid, _, _ = fast_loglik(sub, vecs, n_nodes=6)
     fs = ggp.Forest(sub)
-    fs.set_mode("fast")
+    fs.set_mode(6)
     assert np.max(np.abs(ggp.total_likelihood(vecs, fs) - host) / np.abs(host)) <= 1e-13
     fs.close()
     f.close()
@@ -91,7 +96,7 @@ def test_fast_falls_back_to_strict_outside_its_validity_range():
     vecs = np.stack([P, wide, P * 1.01, bad])
     f = ggp.Forest(d)
     strict, pc_s = ggp.total_likelihood(vecs, f, per_cell=True, raise_on_nan=False)
-    f.set_mode("fast")
+    f.set_mode(6)
     fast, pc_f = ggp.total_likelihood(vecs, f, per_cell=True, raise_on_nan=False)
     assert f.last_strict_reruns == 2
     assert fast[1] == strict[1] and same_bits(pc_f[1], pc_s[1]) and np.isnan(fast[3]) and np.isnan(strict[3])
@@ -101,11 +106,14 @@ def test_fast_falls_back_to_strict_outside_its_validity_range():
     with pytest.raises(ggp.LikelihoodNaN) as e:
         ggp.total_likelihood(vecs, f)
     assert e.value.vec_index == 3 and (e.value.cell, e.value.t_index) == o.nan
-    # more nodes widen the range: with 10 nodes gamma_q = 2 ... still outside (7 > 4); gamma_q = 0.25 is inside
+    # more nodes widen the range (gamma_q = 0.25: the exponent varies by ~0.95 over a step): "fast" chooses 8 nodes; a forced
+    # 5-node rule climbs the ladder 5 -> 6 -> 8 without reaching the strict kernels
     wide[4] = 0.25
-    f.set_mode(10)
-    ll10 = ggp.total_likelihood(wide, f)
-    assert f.last_strict_reruns == 0
+    f.set_mode("fast")
+    ll_w = ggp.total_likelihood(wide, f)
+    assert f.last_strict_reruns == 0 and f.last_fast_nodes == 8
+    f.set_mode(5)
+    assert ggp.total_likelihood(wide, f) == ll_w and f.last_strict_reruns == 0
     f.set_mode("strict")
-    assert rel(ll10, ggp.total_likelihood(wide, f)) <= GATE
+    assert rel(ll_w, ggp.total_likelihood(wide, f)) <= GATE
     f.close()

@@ -276,6 +276,7 @@ def run_ours(args):
     stream = torch.cuda.current_stream()
     forest.set_stream(stream.cuda_stream)
     n_ctp = forest.n_ctp
+    n_cells_gpu = forest.n_cells
     d_params = torch.tensor(P, dtype=torch.float64, device="cuda").reshape(1, 11)
     d_out = torch.zeros(1, dtype=torch.float64, device="cuda")
     total = torch.zeros(1, dtype=torch.float64, device="cuda")
@@ -365,6 +366,7 @@ def run_ours(args):
 
     # strong scaling: ONE forest (the rank-0 seed) partitioned over the ranks by tree, statistics of the whole forest
     strong = None
+    whole = None
     if world > 1:
         whole = ggp.simulate_forest(args.trees, args.generations, seed=20261018)
         whole.init_f, whole.init_r = whole.init_stats()
@@ -382,6 +384,19 @@ def run_ours(args):
                           "(sharding.partition_roots), scalar all-reduce per step; value = ctp of the whole forest / max-over-ranks time"
                           % (args.trees, world))
         fs.close()
+
+    # one process, N GPUs (ggp_group): the other ranks leave, rank 0 drives every device through ONE handle
+    one_process = None
+    if world > 1:
+        forest.close()
+        forest = None
+        torch.cuda.empty_cache()
+        barrier()
+        dist.destroy_process_group()
+        if rank != 0:
+            return
+        time.sleep(1.0)   # let the other ranks release their devices
+        one_process = measure_one_process(ggp, torch, world, args, whole, P)
 
     if rank == 0:
         peak = np.zeros(1)
@@ -422,7 +437,7 @@ def run_ours(args):
 
         line = {"metric": METRIC, "unit": "ctp/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "ctp_total": ctp_total, "cells_per_gpu": forest.n_cells}
+                "ctp_total": ctp_total, "cells_per_gpu": n_cells_gpu}
 
         parity = {"gate": GATE, "fast_vs_strict_full_forest": gate_full}
         if not args.no_cpu_baseline and world == 1:
@@ -474,6 +489,8 @@ def run_ours(args):
         line["roofline_" + other] = roofline(other)
         if strong:
             line["strong"] = strong
+        if one_process:
+            line["one_process"] = one_process
         if not args.no_configs and world == 1:
             forest.close()
             forest = None
@@ -483,8 +500,39 @@ def run_ours(args):
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if forest is not None:
         forest.close()
-    if world > 1:
-        dist.destroy_process_group()
+
+
+def measure_one_process(ggp, torch, n_dev, args, whole, P):
+    """ONE host process driving all N GPUs through the library's group handle (ggp_group): strong scaling of the configs[1]
+    evaluation, and configs[2] (-p on 1 M cells) sharded over the devices with every prediction row landing in one pinned
+    host buffer (host parameters in, all rows out, wall clock)"""
+    out = {"what": "rank 0 alone, ggp_group over %d devices: trees split into contiguous runs, one host thread per shard, log-likelihoods "
+                   "added on the host in shard order, prediction rows copied by each device straight into their place" % n_dev}
+    g = ggp.ForestGroup(whole, list(range(n_dev)))
+    for mode in ("strict", "fast"):
+        g.set_mode(mode)
+        for _ in range(3):
+            ll = g.total_likelihood(P)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            ll = g.total_likelihood(P)
+        dt = (time.perf_counter() - t0) / args.steps
+        out["loglik_" + mode] = {"ms_per_eval": dt * 1e3, "ctp_per_s": whole.n_ctp / dt, "loglik": float(ll)}
+    g.close()
+    data = ggp.simulate_forest(15873, 6, noise_model="scaled", division_model="binomial", seed=20261018)
+    g = ggp.ForestGroup(data, list(range(n_dev)))
+    pins = {k: torch.empty((data.n_ctp, 14), dtype=torch.float64).pin_memory().numpy() for k in ("forward", "backward", "prediction")}
+    Pp = np.ascontiguousarray(ggp.PARAMS_SCALED_BINOMIAL.reshape(1, 11))
+    ts = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        g.predictions(Pp, packed=True, out=pins)
+        ts.append(time.perf_counter() - t0)
+    out["cfg3_predict_sharded"] = {"n_cells": int(data.n_cells), "n_ctp": int(data.n_ctp), "e2e_ms": float(np.min(ts[1:])) * 1e3,
+                                   "ctp_per_s": data.n_ctp / float(np.min(ts[1:])), "d2h_bytes": int(3 * 14 * 8 * data.n_ctp),
+                                   "finite": bool(np.isfinite(pins["prediction"][::997]).all())}
+    g.close()
+    return out
 
 
 def measure_configs(ggp, _lib, lib, torch, device, fp64_peak):

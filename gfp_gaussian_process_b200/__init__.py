@@ -7,7 +7,7 @@ Host-side mirror of the reference's entry points (same names and argument meanin
   collect_joint_distributions   correlation_tree.h:629
 All numerical work is done by libggp_b200.so (hand-written CUDA); there is no CPU fallback.
 """
-from .forest import Forest, LineageData, NOISE_MODELS, DIVISION_MODELS, PARAM_NAMES  # noqa: F401
+from .forest import Forest, ForestGroup, LineageData, NOISE_MODELS, DIVISION_MODELS, PARAM_NAMES  # noqa: F401
 from .api import (total_likelihood, prediction_forward_backward, run_bound_1dscan, arange,  # noqa: F401
                   num_hessian_ll, LikelihoodNaN, collect_joint_distributions, prediction_upper14, count_joints)
 from .synthetic import simulate_forest, PARAMS_CONST_GAUSS, PARAMS_SCALED_BINOMIAL  # noqa: F401

@@ -55,6 +55,17 @@ SIGNATURES = {
     "ggp_forest_n_roots": (C.c_int64, [C.c_void_p]),
     "ggp_forest_n_generations": (C.c_int64, [C.c_void_p]),
     "ggp_forest_get_init": (C.c_int, [C.c_void_p, c_double_p, c_double_p]),
+    "ggp_group_create": (C.c_int, [C.POINTER(ForestDesc), c_int32_p, C.c_int32, C.POINTER(C.c_void_p)]),
+    "ggp_group_destroy": (None, [C.c_void_p]),
+    "ggp_group_size": (C.c_int32, [C.c_void_p]),
+    "ggp_group_is_contiguous": (C.c_int32, [C.c_void_p]),
+    "ggp_group_member": (C.c_void_p, [C.c_void_p, C.c_int32]),
+    "ggp_group_member_cells": (C.c_int64, [C.c_void_p, C.c_int32, c_int64_p]),
+    "ggp_group_member_ctp": (C.c_int64, [C.c_void_p, C.c_int32, c_int64_p]),
+    "ggp_group_set_mode": (C.c_int, [C.c_void_p, C.c_int32]),
+    "ggp_group_loglik": (C.c_int, [C.c_void_p, c_double_p, C.c_int32, c_double_p, c_double_p, c_double_p, C.POINTER(NanInfo)]),
+    "ggp_group_predict": (C.c_int, [C.c_void_p, c_double_p, C.c_int32, c_double_p, c_double_p, c_double_p]),
+    "ggp_group_predict14": (C.c_int, [C.c_void_p, c_double_p, C.c_int32, c_double_p, c_double_p, c_double_p]),
     "ggp_forest_set_mode": (C.c_int, [C.c_void_p, C.c_int32]),
     "ggp_forest_get_mode": (C.c_int32, [C.c_void_p]),
     "ggp_last_fast_nodes": (C.c_int32, [C.c_void_p]),

@@ -125,32 +125,37 @@ def build_daughters(parent):
     return d1, d2
 
 
+def _make_desc(data: LineageData, device: int = 0):
+    d = _lib.ForestDesc()
+    d.n_cells, d.n_ctp = data.n_cells, data.n_ctp
+    d.cell_offset = data.cell_offset.ctypes.data_as(_lib.c_int64_p)
+    d.parent = data.parent.ctypes.data_as(_lib.c_int32_p)
+    d.daughter1 = data.daughter1.ctypes.data_as(_lib.c_int32_p)
+    d.daughter2 = data.daughter2.ctypes.data_as(_lib.c_int32_p)
+    d.time = data.time.ctypes.data_as(_lib.c_double_p)
+    d.log_length = data.log_length.ctypes.data_as(_lib.c_double_p)
+    d.fp = data.fp.ctypes.data_as(_lib.c_double_p)
+    d.segment = data.segment.ctypes.data_as(_lib.c_int32_p)
+    d.noise_model = NOISE_MODELS[data.noise_model]
+    d.division_model = DIVISION_MODELS[data.division_model]
+    d.fp_auto = data.fp_auto
+    if data.init_f is not None and data.init_r is not None:
+        d.init_f = (C.c_double * 4)(*[float(v) for v in data.init_f])
+        d.init_r = (C.c_double * 4)(*[float(v) for v in data.init_r])
+        d.compute_init = 0
+    else:
+        d.compute_init = 1
+    d.device = device
+    return d
+
+
 class Forest:
     """Device-resident forest (ggp_forest handle)."""
 
     def __init__(self, data: LineageData, device: int = 0):
         self._lib = _lib.load()
         self.data = data
-        d = _lib.ForestDesc()
-        d.n_cells, d.n_ctp = data.n_cells, data.n_ctp
-        d.cell_offset = data.cell_offset.ctypes.data_as(_lib.c_int64_p)
-        d.parent = data.parent.ctypes.data_as(_lib.c_int32_p)
-        d.daughter1 = data.daughter1.ctypes.data_as(_lib.c_int32_p)
-        d.daughter2 = data.daughter2.ctypes.data_as(_lib.c_int32_p)
-        d.time = data.time.ctypes.data_as(_lib.c_double_p)
-        d.log_length = data.log_length.ctypes.data_as(_lib.c_double_p)
-        d.fp = data.fp.ctypes.data_as(_lib.c_double_p)
-        d.segment = data.segment.ctypes.data_as(_lib.c_int32_p)
-        d.noise_model = NOISE_MODELS[data.noise_model]
-        d.division_model = DIVISION_MODELS[data.division_model]
-        d.fp_auto = data.fp_auto
-        if data.init_f is not None and data.init_r is not None:
-            d.init_f = (C.c_double * 4)(*[float(v) for v in data.init_f])
-            d.init_r = (C.c_double * 4)(*[float(v) for v in data.init_r])
-            d.compute_init = 0
-        else:
-            d.compute_init = 1
-        d.device = device
+        d = _make_desc(data, device)
         h = C.c_void_p()
         _lib.check(self._lib.ggp_forest_create(C.byref(d), C.byref(h)))
         self._h = h
@@ -233,3 +238,77 @@ class Forest:
     @property
     def last_launch_count(self):
         return self._lib.ggp_last_launch_count(self._h)
+
+
+class ForestGroup:
+    """One data set sharded over several GPUs behind one handle (ggp_group): one host process drives them all."""
+
+    def __init__(self, data: LineageData, devices):
+        self._lib = _lib.load()
+        self.data = data
+        d = _make_desc(data, 0)
+        dev = (C.c_int32 * len(devices))(*[int(v) for v in devices])
+        h = C.c_void_p()
+        _lib.check(self._lib.ggp_group_create(C.byref(d), dev, len(devices), C.byref(h)))
+        self._h = h
+        self.n_cells, self.n_ctp, self.n_roots = data.n_cells, data.n_ctp, len(data.roots())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.ggp_group_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    @property
+    def size(self):
+        return self._lib.ggp_group_size(self._h)
+
+    @property
+    def contiguous(self):
+        return bool(self._lib.ggp_group_is_contiguous(self._h))
+
+    def member_ctp(self, k):
+        n = self._lib.ggp_group_member_ctp(self._h, k, None)
+        a = np.empty(n, dtype=np.int64)
+        self._lib.ggp_group_member_ctp(self._h, k, a.ctypes.data_as(_lib.c_int64_p))
+        return a
+
+    def set_mode(self, mode):
+        code = {"strict": _lib.GGP_MODE_STRICT, "fast": _lib.GGP_MODE_FAST}.get(mode, mode)
+        _lib.check(self._lib.ggp_group_set_mode(self._h, int(code)))
+
+    def total_likelihood(self, params_vec, root_carry=None, per_cell=False):
+        p = np.ascontiguousarray(params_vec, dtype=np.float64)
+        single = p.ndim == 1
+        p = p.reshape(-1, _lib.N_PARAMS)
+        n_vec = p.shape[0]
+        out = np.empty(n_vec)
+        cell_ll = np.empty((n_vec, self.n_cells)) if per_cell else None
+        nan = (_lib.NanInfo * n_vec)()
+        rc = self._lib.ggp_group_loglik(self._h, p.ctypes.data_as(_lib.c_double_p), n_vec,
+                                        root_carry.ctypes.data_as(_lib.c_double_p) if root_carry is not None else None,
+                                        out.ctypes.data_as(_lib.c_double_p),
+                                        cell_ll.ctypes.data_as(_lib.c_double_p) if per_cell else None, nan)
+        _lib.check(rc, allow=(_lib.GGP_ERR_NAN,))
+        self.nan = [(nan[v].cell, nan[v].t_index) for v in range(n_vec)]
+        res = out[0] if single else out
+        return (res, (cell_ll[0] if single else cell_ll)) if per_cell else res
+
+    def predictions(self, params_vecs, packed=False, out=None):
+        """forward / backward / combined for the whole data set in the caller's order; packed: 14 columns per time point"""
+        p = np.ascontiguousarray(params_vecs, dtype=np.float64).reshape(-1, _lib.N_PARAMS)
+        w = 14 if packed else 20
+        bufs = out or {k: np.empty((self.n_ctp, w)) for k in ("forward", "backward", "prediction")}
+        fn = self._lib.ggp_group_predict14 if packed else self._lib.ggp_group_predict
+        _lib.check(fn(self._h, p.ctypes.data_as(_lib.c_double_p), p.shape[0], *[bufs[k].ctypes.data_as(_lib.c_double_p) if k in bufs else None
+                                                                               for k in ("forward", "backward", "prediction")]))
+        return bufs

@@ -77,6 +77,10 @@ struct LoglikResult {
     throw std::domain_error("Likelihood is Nan");
 }
 
+// --fast: likelihood evaluations of -m / -s use the library's fast arithmetic (GGP_MODE_FAST: quadrature + FMA, within 1e-10 of
+// the reference's log-likelihood, not bit-identical); implies --fresh, predictions and joints stay strict
+static bool g_fast_likelihood = false;
+
 // one data slice on one device + the roots' persistent covariance (the reference's MOMAdata::cov of the roots)
 class DeviceForest : public Forest {
 public:
@@ -88,6 +92,7 @@ public:
             for (int i = 0; i < 4; ++i) { d.init_f[i] = init_f[i]; d.init_r[i] = init_r[i]; }
         }
         check(ggp_forest_create(&d, &h_), "ggp_forest_create");
+        if (g_fast_likelihood) check(ggp_forest_set_mode(h_, GGP_MODE_FAST), "ggp_forest_set_mode");
         carry_.assign((size_t)ggp_forest_n_roots(h_) * 16, 0.0);
     }
     ~DeviceForest() override { ggp_forest_destroy(h_); }
@@ -637,6 +642,7 @@ Args arg_parser(int argc, char** argv) {
         {"-d", "--device", "(ggp-b200) CUDA device ordinal, default: 0"},
         {"-ds", "--devices", "(ggp-b200) comma separated CUDA device ordinals: lineage trees are sharded over them"},
         {"-fresh", "--fresh", "(ggp-b200) history-free evaluations, speculative batching of simplex moves"},
+        {"-fast", "--fast", "(ggp-b200) fast likelihood arithmetic for -m / -s (within 1e-10 of the reference, not bit-identical); implies --fresh"},
         {"-sj", "--sparse_joints", "(ggp-b200) write one line per joint instead of the dense matrix"},
         {"-corr", "--correlation", "(ggp-b200) time between measurements: correlation functions straight from the joints (implies -p; no joints file)"},
         {"-n_data", "--n_data", "(ggp-b200) number of lags of the correlation function, default: 200"},
@@ -674,6 +680,7 @@ Args arg_parser(int argc, char** argv) {
             else if (key == "-d") a["device"] = value(i);
             else if (key == "-ds") a["devices"] = value(i);
             else if (key == "-fresh") a["fresh"] = "1";
+            else if (key == "-fast") { a["fast"] = "1"; a["fresh"] = "1"; }
             else if (key == "-sj") a["sparse_joints"] = "1";
             else if (key == "-corr") { a["correlation"] = value(i); a["predict"] = "1"; }
             else if (key == "-n_data") a["n_data"] = value(i);
@@ -717,6 +724,7 @@ int main(int argc, char** argv) {
         S.devices.clear();
         for (const auto& d : split(S.args.count("devices") ? S.args["devices"] : S.args["device"], ",")) S.devices.push_back(std::stoi(trim(d)));
         S.fresh = S.args.count("fresh") > 0;
+        g_fast_likelihood = S.args.count("fast") > 0;
         const std::string log_base = out_dir(S.args) + file_base(S.args["infile"]);
         outfile_log = log_base + ".log";
         outfile_log_success = log_base + "_success.log";

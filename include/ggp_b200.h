@@ -157,6 +157,30 @@ int ggp_predict14(ggp_forest* f, const double* params, int32_t n_seg,
 int ggp_joints(ggp_forest* f, const double* params, int32_t n_seg, double rel_tol, int64_t row_begin, int64_t row_end,
                int64_t cap, int64_t* out_count, int64_t* row_ctp, int64_t* col_ctp, double* rec44);
 
+/* ---- one host process, several GPUs (SURVEY.md 8b "Threading", 8e) ---------------------------------------------------------
+ * A group shards the lineage trees of ONE data set over devices behind one handle: every shard is a ggp_forest on its own
+ * device (own streams, one host thread per shard inside a call), created with the init_cells statistics of the whole data set;
+ * the per-shard log-likelihoods are added on the host in shard order (reproducible; 8 bytes per vector need no collective),
+ * per-cell sums, root_carry and prediction rows come back in the caller's order.  A data set stored tree by tree is split into
+ * contiguous runs of trees, so each device copies its prediction rows straight into their place in the caller's arrays;
+ * otherwise trees are bin-packed by size and the rows are scattered back by index.  Same argument meaning and error
+ * behaviour as the single-forest calls; joints run per member (ggp_group_member + ggp_group_member_ctp give the handles and
+ * the index maps).  `devices` may name a device more than once. */
+typedef struct ggp_group ggp_group;
+int ggp_group_create(const ggp_forest_desc* desc, const int32_t* devices, int32_t n_devices, ggp_group** out);   /* desc->device is ignored */
+void ggp_group_destroy(ggp_group* g);
+int32_t ggp_group_size(const ggp_group* g);
+int32_t ggp_group_is_contiguous(const ggp_group* g);
+ggp_forest* ggp_group_member(ggp_group* g, int32_t k);                             /* NULL: shard k holds no tree */
+int64_t ggp_group_member_cells(const ggp_group* g, int32_t k, int64_t* cells);     /* caller's cell index of the shard's cells; NULL: count only */
+int64_t ggp_group_member_ctp(const ggp_group* g, int32_t k, int64_t* ctp);         /* caller's time-point index of the shard's time points */
+int ggp_group_set_mode(ggp_group* g, int32_t mode);
+int ggp_group_loglik(ggp_group* g, const double* params, int32_t n_vec, double* root_carry, double* out_loglik,
+                     double* out_cell_ll, ggp_nan_info* nan);
+int ggp_group_predict(ggp_group* g, const double* params, int32_t n_seg, double* out_forward, double* out_backward, double* out_combined);
+int ggp_group_predict14(ggp_group* g, const double* params, int32_t n_seg, double* out_forward14, double* out_backward14,
+                        double* out_combined14);
+
 /* waits for the evaluation enqueued by ggp_loglik_device and returns its device time in milliseconds */
 int ggp_sync_kernel_ms(ggp_forest* f, double* ms_out);
 

@@ -137,6 +137,26 @@ def test_fresh_mode_speculative_search_reaches_the_same_optimum(tmp_path):
         assert abs(o.total_loglik(row[:11]) - row[11]) <= 1e-10 * abs(row[11])   # fresh: a pure function of the parameters
 
 
+def test_fast_option_stays_inside_the_gate_on_every_logged_evaluation(tmp_path):
+    """--fast: -m and -s with the fast likelihood arithmetic; every evaluation the command line logged is within 1e-10 of
+    the oracle's value for the same parameters, and the predictions written afterwards are still the strict ones"""
+    P = ggp.PARAMS_CONST_GAUSS
+    data = ggp.simulate_forest(8, 3, seed=22)
+    csv, cfg = write_inputs(tmp_path, data)
+    pf = write_params(tmp_path / "p.txt", P * np.array([1.2, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1]), free=(0,))
+    out = str(tmp_path / "f")
+    run(["-i", csv, "-b", pf, "-c", cfg, "-m", "-p", "-t", "1e-6", "-noise", "const", "-div", "gauss", "-o", out, "--fast"])
+    it = read_table(os.path.join(out, "forest_f0_b_iterations.csv"), "iteration,")
+    rows = np.array([[float(x) for x in r[1:]] for r in it])
+    o = Oracle(data)
+    for row in rows[:8]:
+        assert abs(o.total_loglik(row[:11]) - row[11]) <= 1e-10 * abs(row[11])
+    out2 = str(tmp_path / "s")
+    run(["-i", csv, "-b", pf, "-c", cfg, "-m", "-p", "-t", "1e-6", "-noise", "const", "-div", "gauss", "-o", out2, "--fresh"])
+    rows2 = np.array([[float(x) for x in r[1:]] for r in read_table(os.path.join(out2, "forest_f0_b_iterations.csv"), "iteration,")])
+    assert abs(rows[np.argmax(rows[:, 11])][0] - rows2[np.argmax(rows2[:, 11])][0]) < 1e-6 * abs(rows2[0][0])
+
+
 def test_joints_files_dense_and_sparse(tmp_path):
     P = ggp.PARAMS_SCALED_BINOMIAL
     data = ggp.simulate_forest(2, 3, noise_model="scaled", division_model="binomial", seed=15, pts_range=(3, 5))

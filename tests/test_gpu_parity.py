@@ -396,6 +396,51 @@ def test_sharded_predictions_and_joints_gather_to_the_unsharded_result():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("ragged", [False, True])
+def test_group_handle_shards_one_data_set_over_devices(ragged):
+    """ggp_group: one handle, several shards (here three on the visible devices, wrapping around): per-cell sums, the carry
+    chain, NaN reports and prediction rows come back in the caller's order, bit-identical to the single-forest results;
+    tree-major data is split into contiguous runs (rows copied straight into place), other data is bin-packed and scattered"""
+    import torch
+    nd = max(torch.cuda.device_count(), 1)
+    devices = [k % nd for k in range(3)]
+    if ragged:
+        d = ragged_forest()
+        P = np.stack([ggp.PARAMS_SCALED_BINOMIAL, ggp.PARAMS_SCALED_BINOMIAL * np.array([1, 1, 1, 2, 1, 1, 1, 1, 1, 1, 1.])])
+    else:
+        d = ggp.simulate_forest(23, 4, noise_model="scaled", division_model="binomial", seed=77)
+        P = np.stack([ggp.PARAMS_SCALED_BINOMIAL])
+    g = ggp.ForestGroup(d, devices)
+    assert g.size == 3 and g.contiguous == (not ragged)
+    assert np.array_equal(np.sort(np.concatenate([g.member_ctp(k) for k in range(3)])), np.arange(d.n_ctp))
+    f = ggp.Forest(d)
+    vecs = np.stack([P[0], P[0] * 1.02, P[0] * 0.97])
+    ll_g, pc_g = g.total_likelihood(vecs, per_cell=True)
+    ll_f, pc_f = ggp.total_likelihood(vecs, f, per_cell=True)
+    assert same_bits(pc_g, pc_f) and max_rel(ll_g, ll_f) < 1e-14
+    c_g, c_f = np.zeros((f.n_roots, 16)), np.zeros((f.n_roots, 16))
+    a = g.total_likelihood(vecs, root_carry=c_g, per_cell=True)[1]
+    b = ggp.total_likelihood(vecs, f, root_carry=c_f, per_cell=True)[1]
+    assert same_bits(a, b) and same_bits(c_g, c_f)
+    bad = P[0].copy()
+    bad[7] = -1.0
+    g.total_likelihood(np.stack([P[0], bad]))
+    o = Oracle(d)
+    assert np.isnan(o.total_loglik(bad)) and g.nan[0] == (-1, -1) and g.nan[1] == o.nan
+    full = ggp.prediction_forward_backward(f, P)
+    got = g.predictions(P)
+    got14 = g.predictions(P, packed=True)
+    iu = [4 * i + j for i in range(4) for j in range(i, 4)]
+    for k in ("forward", "backward", "prediction"):
+        assert same_bits(got[k][:, :4], full[k][0]) and same_bits(got[k][:, 4:], full[k][1].reshape(-1, 16))
+        assert same_bits(got14[k][:, :4], full[k][0]) and same_bits(got14[k][:, 4:], full[k][1].reshape(-1, 16)[:, iu])
+    g.set_mode("fast")
+    assert max_rel(g.total_likelihood(vecs), ll_f) <= 1e-10
+    g.close()
+    f.close()
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("seed", [101, 102, 103, 104])
 def test_random_forests_all_passes_bitwise(seed):
     """random shapes (tree counts that do not fill a 32-cell group, very short and long cells, 1-3 segments, both models):

@@ -598,7 +598,15 @@ def measure_configs(ggp, _lib, lib, torch, device, fp64_peak):
     t0 = time.perf_counter()
     r, c, m, v = ggp.collect_joint_distributions(f, P2, 1e-10, row_begin=0, row_end=rows)
     rec_s = time.perf_counter() - t0
+    ts = []
+    for _ in range(2):
+        t0 = time.perf_counter()
+        sums, nj2 = ggp.api.correlation_sums(f, P2, 15.0, 200)
+        ts.append(time.perf_counter() - t0)
     out["cfg5_joints"] = {"n_cells": int(data.n_cells), "n_ctp": int(data.n_ctp), "joints": int(n_j), "prep_ms": prep_ms,
+                          "reduced_ms": float(np.min(ts)) * 1e3, "reduced_joints_per_s": nj2 / float(np.min(ts)),
+                          "reduced_what": "ggp_correlation_sums: walk + lag-binned moment sums of the correlation functions (200 lags) on the "
+                                          "device, 80 kB of sums to the host, no record leaves the GPU",
                           "walk_ms": float(np.min(walk)), "joints_per_s": n_j / (np.min(walk) * 1e-3), "flop_per_joint": F_ALG_JOINT,
                           "frac": n_j * F_ALG_JOINT / (np.min(walk) * 1e-3) / 1e12 / fp64_peak,
                           "records_per_s": len(r) / rec_s, "records": int(len(r)),

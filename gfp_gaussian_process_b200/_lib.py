@@ -55,6 +55,8 @@ SIGNATURES = {
     "ggp_forest_n_roots": (C.c_int64, [C.c_void_p]),
     "ggp_forest_n_generations": (C.c_int64, [C.c_void_p]),
     "ggp_forest_get_init": (C.c_int, [C.c_void_p, c_double_p, c_double_p]),
+    "ggp_correlation_sums": (C.c_int, [C.c_void_p, c_double_p, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_double, C.c_int32,
+                                       c_double_p, c_double_p, c_int64_p]),
     "ggp_group_create": (C.c_int, [C.POINTER(ForestDesc), c_int32_p, C.c_int32, C.POINTER(C.c_void_p)]),
     "ggp_group_destroy": (None, [C.c_void_p]),
     "ggp_group_size": (C.c_int32, [C.c_void_p]),

@@ -180,6 +180,21 @@ def count_joints(forest: Forest, params_vecs, tolerance_joint=1e-10, row_begin=0
     return cnt.value
 
 
+def correlation_sums(forest: Forest, params_vecs, dt_step, n_bins, tolerance_joint=1e-10, atol=None, normalize_time=False):
+    """lag-binned moment sums of the correlation functions, accumulated on the device (ggp_correlation_sums): what
+    python_src/correlation_from_joint.py accumulates from the joints and prediction files.  Returns (sums [n_bins][50] as
+    numpy longdouble, number of emitted joints); prediction_forward_backward must have run with the same params_vecs."""
+    lib = _lib.load()
+    p, _ = _as_params(params_vecs)
+    hi, lo = np.zeros((n_bins, 50)), np.zeros((n_bins, 50))
+    nj = C.c_int64(0)
+    _lib.check(lib.ggp_correlation_sums(forest.handle, p.ctypes.data_as(_lib.c_double_p), p.shape[0], C.c_double(tolerance_joint),
+                                        C.c_double(dt_step), n_bins, C.c_double(0.2 * dt_step if atol is None else atol),
+                                        1 if normalize_time else 0, hi.ctypes.data_as(_lib.c_double_p), lo.ctypes.data_as(_lib.c_double_p),
+                                        C.byref(nj)))
+    return hi.astype(np.longdouble) + lo.astype(np.longdouble), nj.value
+
+
 def backward_cell_state(forest: Forest):
     """each cell's MOMAdata::mean/cov as the backward pass leaves them (sign-flipped frame)."""
     lib = _lib.load()

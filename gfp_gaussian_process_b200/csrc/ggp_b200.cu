@@ -1066,4 +1066,5 @@ int ggp_debug_phase_clocks(unsigned long long* out, int reset) {
 }  // extern "C"
 
 #include "ggp_joints_host.inc"
+#include "ggp_corr.inc"
 #include "ggp_group.inc"

@@ -595,6 +595,30 @@ void run_correlation(Session& S, Forest& Fx, std::vector<ParameterSet>& list) {
         whole.reset(new DeviceForest(T, S.devices[0]));
         handle = whole->handle();
     }
+    CorrelationSet CS = make_correlation_set(S);
+    // the lag-binned sums are accumulated on the device (ggp_correlation_sums: neither a joints file nor a record leaves the GPU);
+    // the host reduction of the sparse records remains for what the device path refuses (more than 256 lags, parents stored
+    // after their daughters) and for GGP_B200_CORR_HOST=1 (A/B comparison)
+    bool on_device = false;
+    if (!getenv("GGP_B200_CORR_HOST")) {
+        // run_prediction_segments has left the predictions on the data set's own handle; a handle made here needs them first
+        if (whole) check(ggp_predict(handle, P.data(), (int32_t)list.size(), nullptr, nullptr, nullptr), "ggp_predict");
+        std::vector<double> hi(CS.bins.size() * 50), lo(CS.bins.size() * 50);
+        int64_t n_joints = 0;
+        const double step = CS.bins.size() > 1 ? CS.bins[1].dt - CS.bins[0].dt : 1.0;
+        const int rc = ggp_correlation_sums(handle, P.data(), (int32_t)list.size(), tol, step, (int32_t)CS.bins.size(), CS.tol,
+                                            S.args.count("normalize_time") > 0, hi.data(), lo.data(), &n_joints);
+        if (rc == GGP_OK) {
+            CS.set_sums(hi.data(), lo.data());
+            S.log << "   " << n_joints << " joints reduced into " << CS.bins.size() << " lag bins on the device\n";
+            on_device = true;
+        } else if (rc != GGP_ERR_BAD_ARG) {
+            check(rc, "ggp_correlation_sums");
+        } else {
+            S.log << "   device reduction not applicable (" << ggp_last_error() << "): host reduction\n";
+        }
+    }
+    if (!on_device) {
     comb.resize((size_t)T.n_ctp() * 20);
     check(ggp_predict(handle, P.data(), (int32_t)list.size(), nullptr, nullptr, comb.data()), "ggp_predict");
     std::vector<double> m14((size_t)T.n_ctp() * 14);
@@ -613,8 +637,8 @@ void run_correlation(Session& S, Forest& Fx, std::vector<ParameterSet>& list) {
         fetch_joints(handle, P, (int)list.size(), tol, r0, r1, row, col, rec, n);
         row.resize(n); col.resize(n);
     };
-    CorrelationSet CS = make_correlation_set(S);
     correlation_from_joints(CS, T.cell_id, T.parent_id, T.offset, T.time, src, S.args.count("normalize_time") > 0, kJointRowBlock);
+    }
     CS.finalize();
     const std::string outfile = prediction_base(S, list) + "_correlations.csv";
     S.log << "Outfile: " << outfile << "\n";

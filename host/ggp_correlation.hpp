@@ -162,6 +162,24 @@ public:
         for (Correlation& b : bins)
             if (std::fabs(b.dt - dt) <= tol + 1e-5 * std::fabs(dt)) { b.add(G); return; }
     }
+    // moment sums accumulated elsewhere (ggp_correlation_sums): [n_bins][50] = n, m[8], upper(mm)[36], c[2], upper(cc)[3], each as
+    // the leading double of the sum and (lo, may be null) its remainder
+    void set_sums(const double* hi, const double* lo) {
+        for (size_t b = 0; b < bins.size(); ++b) {
+            auto at = [&](int k) { return (long double)hi[50 * b + k] + (lo ? (long double)lo[50 * b + k] : 0.0L); };
+            Correlation& B = bins[b];
+            B.n = (long)llroundl(at(0));
+            for (int i = 0; i < 8; ++i) B.m[i] = at(1 + i);
+            int q = 9;
+            for (int i = 0; i < 8; ++i)
+                for (int j = i; j < 8; ++j) { B.mm[i][j] = at(q); B.mm[j][i] = at(q); ++q; }
+            B.c[0] = at(45); B.c[1] = at(46);
+            B.cc[0][0] = at(47); B.cc[0][1] = at(48); B.cc[1][0] = at(48); B.cc[1][1] = at(49);
+            // a single pair: its second moment IS the product of its first moments (the script's long-double sums give an exact
+            // zero covariance there, hence 0 / 0 in the naive correlation; a product rounded to double would leave a residue)
+            if (B.n == 1) for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) B.cc[i][j] = B.c[j] * B.c[i];
+        }
+    }
     void finalize() {
         for (Correlation& b : bins) { b.average(); b.naive(); }
         for (Correlation& b : bins) b.mle(bins[0]);

@@ -157,6 +157,22 @@ int ggp_predict14(ggp_forest* f, const double* params, int32_t n_seg,
 int ggp_joints(ggp_forest* f, const double* params, int32_t n_seg, double rel_tol, int64_t row_begin, int64_t row_end,
                int64_t cap, int64_t* out_count, int64_t* row_ctp, int64_t* col_ctp, double* rec44);
 
+/* replaces: the accumulation of python_src/correlation_from_joint.py (Correlation.add_gaussian :287-302, files2correlation_function
+ * :443-560 with the product-of-marginals fallback :528-534) on top of collect_joint_distributions: the lag-binned moment sums of
+ * the correlation functions straight from the walk, without a joints file or a record ever leaving the device.
+ * Lag bins k * dt_step, k = 0 .. n_bins - 1 (np.arange(0, dt * n_data, dt)); a pair (row i, column j on i's lineage, j > i, or any
+ * emitted joint) goes to the first bin with |k dt_step - dt| <= atol + 1e-5 |dt| (np.isclose; the script uses atol = 0.2 dt_step),
+ * dt = time[j] - time[i], divided by the row cell's life time if normalize_time; lag 0 takes every point with itself.
+ *   out_sums [n_bins][50] = n, sum m[8], sum (m m^T + C) upper triangle row-major [36], sum c[2], sum c c^T upper [3] with
+ *                           c = g / exp(x), indices 0..3 = z(t + dt), 4..7 = z(t); accumulated with compensation on the device,
+ *                           per-block partials added in long double; each entry is the leading double of its sum,
+ *   out_sums_lo             NULL or [n_bins][50]: the remainder (sum - leading double),
+ *   out_joints              NULL or the number of joints the walk emitted.
+ * Requires a prior ggp_predict with the same params, at most 256 bins, and parents stored before their daughters (else
+ * GGP_ERR_BAD_ARG: reduce the sparse records of ggp_joints on the host, host/ggp_correlation.hpp). */
+int ggp_correlation_sums(ggp_forest* f, const double* params, int32_t n_seg, double rel_tol, double dt_step, int32_t n_bins,
+                         double atol, int32_t normalize_time, double* out_sums, double* out_sums_lo, int64_t* out_joints);
+
 /* ---- one host process, several GPUs (SURVEY.md 8b "Threading", 8e) ---------------------------------------------------------
  * A group shards the lineage trees of ONE data set over devices behind one handle: every shard is a ggp_forest on its own
  * device (own streams, one host thread per shard inside a call), created with the init_cells statistics of the whole data set;

@@ -84,3 +84,69 @@ def test_correlation_straight_from_the_gpu_joints(tmp_path, golden_dir):
         assert np.allclose(tab[:, 21:26][ok], ref[:, 21:26][ok], rtol=2e-4, atol=2e-5)   # inputs of the script carry 6 digits
         fin = np.isfinite(ref[:, 11:21:2])
         assert np.all(np.abs(tab[:, 11:21:2][fin] - ref[:, 11:21:2][fin]) <= 3 * GRID_STEP + 2e-4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("normalize", [False, True])
+def test_lag_bins_accumulated_on_the_device_equal_the_host_reduction(tmp_path, normalize):
+    """ggp_correlation_sums (the walk's records never leave the GPU) against the host reduction of the same sparse joints
+    (host/ggp_correlation.hpp, itself pinned to the reference script above), both at full precision: pair counts exact,
+    naive correlations to 1e-12, grid-search maxima on the same grid point with error bars to 1e-9; four
+    generations deep, 40 lags"""
+    from test_gpu_cli import write_inputs, write_params
+    import gfp_gaussian_process_b200 as ggp
+    P = ggp.PARAMS_SCALED_BINOMIAL
+    d = ggp.simulate_forest(9, 4, params=P, noise_model="scaled", division_model="binomial", seed=61, pts_range=(5, 9))
+    csv, cfg = write_inputs(tmp_path, d)
+    pf = write_params(tmp_path / "p.txt", P)
+    dt = float(d.time[1] - d.time[0])
+    tabs = []
+    for name, env in (("dev", {}), ("host", {"GGP_B200_CORR_HOST": "1"})):
+        out = str(tmp_path / name)
+        r = subprocess.run([CLI, "-i", csv, "-b", pf, "-c", cfg, "--correlation", repr(dt), "--n_data", "40", "-o", out] +
+                           (["--normalize_time"] if normalize else []), capture_output=True, text=True, env={**os.environ, **env})
+        assert r.returncode == 0, r.stdout + r.stderr
+        log = open([os.path.join(out, f) for f in os.listdir(out) if f.endswith("_success.log")][0]).read()
+        assert ("lag bins on the device" in log) == (name == "dev")
+        tabs.append(read_table(os.path.join(out, "forest_f_b_correlations.csv"))[1])
+    dev, host = tabs
+    assert dev.shape == host.shape and np.array_equal(dev[:, -1], host[:, -1]) and dev[:, -1].sum() > 1000
+    ok = np.isfinite(host[:, 21:26])
+    assert np.array_equal(np.isfinite(dev[:, 21:26]), ok)
+    zok = ok[:, :4]
+    assert np.allclose(dev[:, 21:25][zok], host[:, 21:25][zok], rtol=1e-12, atol=1e-13)
+    # the concentration c = g / exp(x) is evaluated in double on the device and in long double by the script / host reduction:
+    # a bin holding a handful of pairs amplifies that 1e-16 by c^2 / var(c); 1e-12 from ten pairs on, 1e-9 below
+    many = ok[:, 4] & (host[:, -1] >= 10)
+    few = ok[:, 4] & (host[:, -1] < 10)
+    assert np.allclose(dev[many, 25], host[many, 25], rtol=1e-12, atol=1e-13) and np.allclose(dev[few, 25], host[few, 25], rtol=1e-9, atol=1e-12)
+    same = np.isclose(dev[:, 11:21:2], host[:, 11:21:2], rtol=0, atol=1e-15)
+    assert same.mean() > 0.98
+    assert np.allclose(dev[:, 12:21:2][same], host[:, 12:21:2][same], rtol=1e-9, atol=1e-300)
+    assert np.allclose(dev[:, 1:11], host[:, 1:11], rtol=1e-6, atol=1e-12)
+
+
+@pytest.mark.gpu
+def test_correlation_sums_at_config4_size():
+    """BASELINE configs[4] (100 k cells, two segments): the device reduction over all 52 M joints; pair counts of every lag
+    equal the closed count (every point pairs once with each earlier point of its lineage at that lag)"""
+    import gfp_gaussian_process_b200 as ggp
+    P = ggp.PARAMS_SCALED_BINOMIAL
+    P2 = np.stack([P, P * np.array([1, 1, 1, 2, 1, 1, 1, 1, 1, 1, 1.])])
+    d = ggp.simulate_forest(1587, 6, params=P, noise_model="scaled", division_model="binomial", seed=20261018, n_segments=2)
+    f = ggp.Forest(d)
+    ggp.prediction_forward_backward(f, P2, forward=False, backward=False, combined=False)
+    dt = 15.0
+    sums, n_joints = ggp.api.correlation_sums(f, P2, dt, 200)
+    assert n_joints == ggp.count_joints(f, P2, 1e-10)
+    # lag k: one pair per point whose lineage reaches back k steps (uniform time grid: depth in points of every point)
+    depth = np.zeros(d.n_ctp, dtype=np.int64)
+    first = d.cell_offset[:-1]
+    n = np.diff(d.cell_offset)
+    for c in range(d.n_cells):   # parents precede daughters in the generator's order
+        base = 0 if d.parent[c] < 0 else depth[d.cell_offset[d.parent[c] + 1] - 1] + 1
+        depth[first[c]:first[c] + n[c]] = base + np.arange(n[c])
+    want = np.array([d.n_ctp] + [(depth >= k).sum() for k in range(1, 200)])
+    assert np.array_equal(np.asarray(sums[:, 0], dtype=np.int64), want)
+    assert np.isfinite(np.asarray(sums, dtype=np.float64)).all()
+    f.close()

@@ -34,7 +34,7 @@ def test_fast_step_on_the_example_data_set(golden_dir):
     data, z = example_data(golden_dir)
     P = np.asarray(z["params"])
     ref = Oracle(data).total_loglik(P)
-    fast, valid, _, _ = fast_loglik(data, P, n_nodes=4)
+    fast, valid, _, _ = fast_loglik(data, P, n_nodes=5)
     assert valid[0] == 1 and abs(fast[0] - ref) / abs(ref) <= GATE
 
 

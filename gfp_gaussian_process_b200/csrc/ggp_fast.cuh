@@ -36,6 +36,25 @@
 #endif
 
 template <class T> struct GgpFx;   // scalar helpers
+
+// Taylor coefficients 1/k!, k = 10 .. 2, of the two short exponentials below.  On the device they live in the constant bank: an
+// FP64 instruction reads such an operand as c[bank][offset], whereas a 64-bit literal costs two move instructions every time
+// it is materialised (the CUDA library's exp inlined once per quadrature node: 308 of the kernel's 2 712 instructions were
+// such moves, 15 % of the executed instructions; profiles/r02_fast5_gen5.txt).
+#define GGP_FEXP_INIT {0x1.27e4fb7789f5cp-22, 0x1.71de3a556c734p-19, 0x1.a01a01a01a01ap-16, 0x1.a01a01a01a01ap-13, 0x1.6c16c16c16c17p-10, \
+                       0x1.1111111111111p-7, 0x1.5555555555555p-5, 0x1.5555555555555p-3, 0.5}
+#if defined(__CUDACC__)
+__constant__ double ggp_fexp_c[9] = GGP_FEXP_INIT;
+#endif
+GGP_HDM double ggp_fexp_k(int i) {
+#if defined(__CUDA_ARCH__)
+    return ggp_fexp_c[i];
+#else
+    constexpr double v[9] = GGP_FEXP_INIT;
+    return v[i];
+#endif
+}
+
 template <> struct GgpFx<double> {
     static GGP_HDM double exp_(double x) { return exp(x); }
     static GGP_HDM double log_(double x) { return log(x); }
@@ -43,7 +62,26 @@ template <> struct GgpFx<double> {
     static GGP_HDM double abs_(double x) { return fabs(x); }
     static GGP_HDM bool finite_(double x) { return x - x == 0.0; }
     static GGP_HDM double ln2() { return 0.6931471805599453; }
+    // exp(x) for |x| <= 0.125: degree-10 Taylor polynomial, truncation 0.125^11 / 11! = 3e-18 relative
+    static GGP_HDM double exp_small_(double x) {
+        double p = ggp_fexp_k(0);
+#pragma unroll
+        for (int i = 1; i < 9; ++i) p = p * x + ggp_fexp_k(i);
+        p = p * x + 1.0;
+        return p * x + 1.0;
+    }
+    // exp(x) for |x| <= 0.01: degree 6, truncation 0.01^7 / 7! = 2e-18 relative
+    static GGP_HDM double exp_tiny_(double x) {
+        double p = ggp_fexp_k(4);
+#pragma unroll
+        for (int i = 5; i < 9; ++i) p = p * x + ggp_fexp_k(i);
+        p = p * x + 1.0;
+        return p * x + 1.0;
+    }
 };
+// range of exp_small_ / exp_tiny_
+#define GGP_FAST_SMALL 0.125
+#define GGP_FAST_TINY 0.01
 
 // largest |d(exponent)/ds| * t a step may have for the N-node rule to integrate s^k exp(lambda s), k = 0..3, over [0, t] and
 // [t, 2t] to 3e-15 relative (measured against mpmath)
@@ -129,20 +167,9 @@ GGP_HD void ggp_fast_consts(GgpFastConsts<T, N>& K, T t, T ml, T gl, T sl2, T mq
     }
 }
 
-// exp(x) for |x| <= 0.01 (degree-6 Taylor polynomial, relative error < 2e-18)
-template <class T>
-GGP_HD T ggp_fast_exp_tiny(T x) {
-    T p = T(1) / T(720);
-    p = p * x + T(1) / T(120);
-    p = p * x + T(1) / T(24);
-    p = p * x + T(1) / T(6);
-    p = p * x + T(0.5);
-    p = p * x + T(1);
-    return p * x + T(1);
-}
-
-// the quadrature sums of one step.  TINY: the two secondary exponents (Cxl s and 2 a t s) stay below 0.01 over the step, their
-// exponentials are polynomials; else the library's exp.  Every sum is one FMA per node against a pre-multiplied constant.
+// the quadrature sums of one step.  TINY: the two secondary exponents (Cxl s and 2 a t s) stay below 0.01 and the main one
+// (a s^2 + B0 s) below 0.125 over the step: all three exponentials of a node are short polynomials; else the library's exp.
+// Every sum is one FMA per node against a pre-multiplied constant.
 template <class T, int N, bool TINY>
 GGP_HD void ggp_fast_moments(const GgpFastConsts<T, N>& K, T a, T B0, T Cxl, T EH, T* __restrict__ M) {
     typedef GgpFx<T> X;
@@ -154,9 +181,9 @@ GGP_HD void ggp_fast_moments(const GgpFastConsts<T, N>& K, T a, T B0, T Cxl, T E
     for (int j = 0; j < N; ++j) {
         const GgpFastNode<T> n = K.node[j];
         const T s = n.s;
-        const T A = X::exp_(a * n.s2 + B0 * s);               // exp(a s^2 + B0 s)
-        const T V = TINY ? ggp_fast_exp_tiny(Cxl * s) : X::exp_(Cxl * s);
-        const T U = TINY ? ggp_fast_exp_tiny(twoat * s) : X::exp_(twoat * s);
+        const T A = TINY ? X::exp_small_(a * n.s2 + B0 * s) : X::exp_(a * n.s2 + B0 * s);   // exp(a s^2 + B0 s)
+        const T V = TINY ? X::exp_tiny_(Cxl * s) : X::exp_(Cxl * s);
+        const T U = TINY ? X::exp_tiny_(twoat * s) : X::exp_(twoat * s);
         const T AW = A * V;                                    // exp(a s^2 + W s), W = B0 + Cxl
         const T H = AW * (U * EH);                             // exp(a s'^2 + W s'), s' = t + s, EH = exp(t (W + a t))
         MB0 += n.w * A; MB1 += n.ws * A;
@@ -189,15 +216,18 @@ GGP_HD bool ggp_fast_propagate(GgpFastState<T>& st, const GgpFastConsts<T, N>& K
     const bool ok = (a >= T(0)) && X::finite_(lam) && (lam * t <= lmax);
 
     // ---- the 19 moments of the step: sum_j w_j s_j^k * (exponential), mean_cov_model.h:9-67 by quadrature ----
-    const T EH = X::exp_(t * (W + a * t));
-    T M[19];
+    // lam t bounds |a s^2 + B s| on [0, t] and |t (W + a t)|: below GGP_FAST_SMALL (every step a rule of at most 5 nodes accepts)
+    // these exponentials are short polynomials as well
     const T sec = X::abs_(Cxl) > T(2) * a * t ? X::abs_(Cxl) : T(2) * a * t;
-    if (sec * t <= T(0.01)) ggp_fast_moments<T, N, true>(K, a, B0, Cxl, EH, M);
+    const bool small = lam * t <= T(GGP_FAST_SMALL);
+    const T EH = small ? X::exp_small_(t * (W + a * t)) : X::exp_(t * (W + a * t));
+    T M[19];
+    if (small && sec * t <= T(GGP_FAST_TINY)) ggp_fast_moments<T, N, true>(K, a, B0, Cxl, EH, M);
     else ggp_fast_moments<T, N, false>(K, a, B0, Cxl, EH, M);
     // exp(c): c0 = bx + Cxx/2 - b t (B-family, mean_cov_model.h:76-115), c5 = 2 (bx + Cxx - b t) (W-family, :124-164)
     const T E1 = X::exp_(bx + T(0.5) * Cxx);
     const T Ec0 = E1 * K.ebt;
-    const T Ec5 = (E1 * K.ebt) * (E1 * K.ebt) * X::exp_(Cxx);
+    const T Ec5 = (E1 * K.ebt) * (E1 * K.ebt) * (X::abs_(Cxx) <= T(GGP_FAST_SMALL) ? X::exp_small_(Cxx) : X::exp_(Cxx));
     const T JB0 = Ec0 * M[0], JB1 = Ec0 * M[1];                        // I_k(B0, c0; 0, t)
     const T JBm0 = Ec0 * M[2], JBm1 = Ec0 * M[3], JBm2 = Ec0 * M[4];   // I_k(B0 - gq, c0; 0, t)
     const T JBs0 = Ec0 * M[5];                                         // I_0(B0 + gq, c0) - I_0(B0 - gq, c0)

@@ -45,8 +45,12 @@ F_ALG_PREDICT = 8900.0   # -p: 2 F_alg + 1 500 (combine)
 F_ALG_JOINT = 5500.0     # -j: per emitted joint
 B_ALG = 28.0          # algorithmic bytes per cell-timepoint: time, x, g (f64) + segment (i32)
 # dram__bytes_read.sum + dram__bytes_write.sum per cell-timepoint from the ncu --set full captures of the largest
-# generation's launch (6 399 691 ctp): strict profiles/r01_s5_loglik_coop_gen5.txt, fast profiles/r02_fast6_gen5.txt
-DRAM_BYTES_PER_CTP_NCU = {"strict": (204.285440e6 + 4.971776e6) / 6399691.0, "fast": (144.504064e6 + 3.952896e6) / 6399691.0}
+# generation's launch (6 399 691 ctp): strict profiles/r01_s5_loglik_coop_gen5.txt, fast profiles/r02_fast5_poly_gen5.txt
+DRAM_BYTES_PER_CTP_NCU = {"strict": (204.285440e6 + 4.971776e6) / 6399691.0, "fast": (144.559872e6 + 4.336640e6) / 6399691.0}
+# what the fast kernel EXECUTES per cell-timepoint with the 5-node rule (same capture: 66.39 M DFMA, 21.49 M DMUL, 9.77 M DADD
+# warp instructions for 6 399 691 ctp), an FMA counted as two flops
+FAST_EXEC = {"nodes": 5, "dfma": 66392317 * 32 / 6399691.0, "dmul": 21490749 * 32 / 6399691.0, "dadd": 9770336 * 32 / 6399691.0,
+             "instr": 134042100 * 32 / 6399691.0, "fp64_pipe_busy": 0.698}
 METRIC = "cell-timepoints/s, FP64 log-likelihood evaluation (loglik evals/s in config)"
 GATE = 1e-10          # north star: log-likelihood within relative 1e-10 of the reference
 
@@ -408,6 +412,16 @@ def run_ours(args):
         except Exception:
             hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
 
+        def executed(r):
+            """executed FP64 work of the fast kernel (ncu instruction counts of the 5-node build; other node counts: none)"""
+            if r["nodes"] != FAST_EXEC["nodes"]:
+                return None
+            flop = 2 * FAST_EXEC["dfma"] + FAST_EXEC["dmul"] + FAST_EXEC["dadd"]
+            ach = n_ctp * flop / (r["kern_ms"] * 1e-3) / 1e12
+            return {"flop_per_ctp": flop, "fp64_instr_per_ctp": FAST_EXEC["dfma"] + FAST_EXEC["dmul"] + FAST_EXEC["dadd"],
+                    "instr_per_ctp": FAST_EXEC["instr"], "achieved": ach, "unit": "TFLOP/s", "frac": ach / fp64_peak,
+                    "fp64_pipe_busy_ncu": FAST_EXEC["fp64_pipe_busy"]}
+
         def roofline(mode):
             r = res[mode]
             ach = n_ctp * F_ALG / (r["kern_ms"] * 1e-3) / 1e12
@@ -419,13 +433,15 @@ def run_ours(args):
                     "kernel": kernel, "kernel_ms_per_step": r["kern_ms"], "flop_per_ctp": F_ALG,
                     "peak_source": "DFMA micro-benchmark run in this process (ggp_fp64_peak); MEASURED_PEAKS.json holds no FP64 figure",
                     "note": ("F_alg counts the reference's formulas (38 integrals via Dawson, 26 exp, 3 pow per step); the fast kernel "
-                             "evaluates the same moments by quadrature with N + 4 exponentials and no Dawson / pow: ~580 executed FP64 "
-                             "instructions per ctp at 6 nodes (ncu), i.e. the fraction is ALGORITHMIC work per second over the DFMA peak, "
-                             "not pipe utilisation (FP64 pipe busy 54-60 %, profiles/r02_fast6_gen5*.txt)") if mode == "fast" else
+                             "evaluates the same moments by quadrature with 3 N short exponentials and no Dawson / pow, so `frac` is "
+                             "ALGORITHMIC work per second over the DFMA peak and exceeds 1; `executed` is what the kernel really does "
+                             "(ncu, 5 nodes: 670 instructions / 488 FP64 per ctp, FP64 pipe 69.8 % busy, profiles/r02_fast5_poly_gen5.txt)")
+                    if mode == "fast" else
                             ("strict arithmetic cannot fuse (FMA off) and evaluates 66 exp + 14 Dawson + 3 pow per step bit for bit: "
                              "3 220 executed FP64 instructions per ctp, FP64 pipe busy 44.5 % (profiles/r01_s5_loglik_coop_gen5.txt)"),
                     "hbm": {"achieved": n_ctp * B_ALG / (r["kern_ms"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                            "frac": n_ctp * B_ALG / (r["kern_ms"] * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src}}
+                            "frac": n_ctp * B_ALG / (r["kern_ms"] * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src},
+                    **({"executed": executed(r)} if mode == "fast" else {})}
 
         def e2e(mode):
             r = res[mode]
@@ -595,9 +611,15 @@ def measure_configs(ggp, _lib, lib, torch, device, fp64_peak):
         n_j = ggp.count_joints(f, P2, 1e-10)
         walk.append(f.last_kernel_ms)
     rows = 100000
-    t0 = time.perf_counter()
-    r, c, m, v = ggp.collect_joint_distributions(f, P2, 1e-10, row_begin=0, row_end=rows)
-    rec_s = time.perf_counter() - t0
+    n_rec = ggp.count_joints(f, P2, 1e-10, 0, rows)
+    pin_rec = (torch.empty(n_rec, dtype=torch.int64).pin_memory().numpy(), torch.empty(n_rec, dtype=torch.int64).pin_memory().numpy(),
+               torch.empty((n_rec, 44), dtype=torch.float64).pin_memory().numpy())
+    rec_ts = []
+    for _ in range(2):
+        t0 = time.perf_counter()
+        r, c, m, v = ggp.collect_joint_distributions(f, P2, 1e-10, row_begin=0, row_end=rows, out=pin_rec)
+        rec_ts.append(time.perf_counter() - t0)
+    rec_s = float(np.min(rec_ts))
     ts = []
     for _ in range(2):
         t0 = time.perf_counter()
@@ -611,7 +633,7 @@ def measure_configs(ggp, _lib, lib, torch, device, fp64_peak):
                           "frac": n_j * F_ALG_JOINT / (np.min(walk) * 1e-3) / 1e12 / fp64_peak,
                           "records_per_s": len(r) / rec_s, "records": int(len(r)),
                           "what": "every start point, count only (walk); records_per_s = the first %d start points with their records sorted "
-                                  "on the device and copied to host arrays" % rows}
+                                  "on the device and copied into pinned host arrays (368 B per record)" % rows}
     f.close()
     return out
 

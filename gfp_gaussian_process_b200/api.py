@@ -146,24 +146,32 @@ def prediction_upper14(forest: Forest, params_vecs, forward=True, backward=True,
     return {k: a for k, a in bufs.items() if a is not None}
 
 
-def collect_joint_distributions(forest: Forest, params_vecs, tolerance_joint=1e-10, row_begin=0, row_end=None, cap=None):
+def collect_joint_distributions(forest: Forest, params_vecs, tolerance_joint=1e-10, row_begin=0, row_end=None, cap=None, out=None):
     """collect_joint_distributions (correlation_tree.h:629-648) as a sparse list instead of the dense CSV.
     prediction_forward_backward must have been run on `forest` with the same params_vecs (the reference's -j
     implies -p, main.cpp:265-268).  Rows are the start points row_begin <= ctp < row_end.
     Returns (row_ctp, col_ctp, mean [n][8], cov_upper [n][36]), sorted by (row, col): the joint of
-    z at `col` (first four means) and z at `row` (last four), tolerance as --rel_tolerance_joints."""
+    z at `col` (first four means) and z at `row` (last four), tolerance as --rel_tolerance_joints.
+    out: optional preallocated (row int64 [cap], col int64 [cap], rec float64 [cap][44]) arrays, e.g. pinned host memory (the
+    copy into fresh pageable numpy arrays is bound by the host's first-touch page faults, not by the GPU)."""
     lib = _lib.load()
     p, _ = _as_params(params_vecs)
     if row_end is None:
         row_end = forest.n_ctp
     cnt = C.c_int64(0)
     args = (forest.handle, p.ctypes.data_as(_lib.c_double_p), p.shape[0], C.c_double(tolerance_joint), row_begin, row_end)
-    if cap is None:
-        _lib.check(lib.ggp_joints(*args, 0, C.byref(cnt), None, None, None))
-        cap = cnt.value
-    row = np.empty(max(cap, 1), dtype=np.int64)
-    col = np.empty(max(cap, 1), dtype=np.int64)
-    rec = np.empty((max(cap, 1), 44))
+    if out is not None:
+        row, col, rec = out
+        cap = min(len(row), len(col), len(rec))
+        if row.dtype != np.int64 or col.dtype != np.int64 or rec.dtype != np.float64 or rec.shape[1:] != (44,) or not rec.flags.c_contiguous:
+            raise ValueError("out = (int64 [cap], int64 [cap], float64 [cap][44])")
+    else:
+        if cap is None:
+            _lib.check(lib.ggp_joints(*args, 0, C.byref(cnt), None, None, None))
+            cap = cnt.value
+        row = np.empty(max(cap, 1), dtype=np.int64)
+        col = np.empty(max(cap, 1), dtype=np.int64)
+        rec = np.empty((max(cap, 1), 44))
     _lib.check(lib.ggp_joints(*args, cap, C.byref(cnt), row.ctypes.data_as(_lib.c_int64_p), col.ctypes.data_as(_lib.c_int64_p),
                               rec.ctypes.data_as(_lib.c_double_p)))
     n = min(cnt.value, cap)

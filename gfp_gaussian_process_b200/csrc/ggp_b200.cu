@@ -152,6 +152,16 @@ struct ggp_forest {
     DevBuf<int> w_invalid;
     DevBuf<double> fwd, bwd, comb, bstate, pred_params, prep, jstack, pack;
     DevBuf<int32_t> ctp_slot, jstack_slot;
+    // scratch of ggp_correlation_sums, kept between calls (a row block's records alone are 1.5 GB: allocating and freeing
+    // them per call cost more than the kernels)
+    struct {
+        DevBuf<long long> row, col;
+        DevBuf<double> rec, partial;
+        DevBuf<unsigned long long> count;
+        DevBuf<unsigned short> key, key2;
+        DevBuf<unsigned int> idx, idx2;
+        DevBuf<unsigned char> tmp;
+    } corr;
     bool have_prep = false;
     bool have_pred = false;
     int32_t pred_n_seg = 0;

@@ -410,13 +410,22 @@ GGP_HD void ggp_emit_joint(const GgpJointArgs& A, int64_t row, int64_t col, cons
     A.row_ctp[idx] = row;
     A.col_ctp[idx] = col;
     double* r = A.rec44 + 44 * idx;
+    double v[44];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) r[i] = J.m[i];
+    for (int i = 0; i < 8; ++i) v[i] = J.m[i];
     int q = 8;
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = i; j < 8; ++j) r[q++] = J.C[8 * i + j];
+        for (int j = i; j < 8; ++j) v[q++] = J.C[8 * i + j];
+#if defined(__CUDA_ARCH__)
+    // a record is 352 bytes at a multiple of 352 from a 256-byte aligned base: 22 sixteen-byte stores instead of 44 eight-byte ones
+    double2* r2 = reinterpret_cast<double2*>(r);
+#pragma unroll
+    for (int i = 0; i < 22; ++i) r2[i] = make_double2(v[2 * i], v[2 * i + 1]);
+#else
+    for (int i = 0; i < 44; ++i) r[i] = v[i];
+#endif
 }
 
 GGP_HD void ggp_load_joint(const double* __restrict__ src, GgpGauss8& J) {

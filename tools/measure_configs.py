@@ -42,8 +42,12 @@ if "cfg1" in which:   # the example data set (one tree, 77 cells, 22 065 points)
     t64 = timed(lambda: ggp.total_likelihood(np.tile(P, (64, 1)), f))
     t400 = timed(lambda: ggp.total_likelihood(np.tile(P, (400, 1)), f))
     tp = timed(lambda: ggp.prediction_forward_backward(f, [P]))
+    f.set_mode("fast")
+    f1 = timed(lambda: ggp.total_likelihood(P, f))
+    f400 = timed(lambda: ggp.total_likelihood(np.tile(P, (400, 1)), f))
     out(config="cfg1 example data set, library calls", n_ctp=int(data.n_ctp), generations=f.n_generations, ms_loglik_1=t1 * 1e3,
-        ms_loglik_64=t64 * 1e3, ms_loglik_400=t400 * 1e3, ms_predict=tp * 1e3)
+        ms_loglik_64=t64 * 1e3, ms_loglik_400=t400 * 1e3, ms_predict=tp * 1e3, ms_fast_loglik_1=f1 * 1e3, ms_fast_loglik_400=f400 * 1e3,
+        fast_nodes=int(f.last_fast_nodes), fast_strict_reruns=int(f.last_strict_reruns))
     f.close()
     from test_gpu_cli import write_inputs, write_params, CLI
     import pathlib
@@ -53,7 +57,7 @@ if "cfg1" in which:   # the example data set (one tree, 77 cells, 22 065 points)
     with open(pf, "w") as fh:   # the example's parameter file: everything free except beta
         for i, (n, v) in enumerate(zip(ggp.PARAM_NAMES, P)):
             fh.write(f"{n} = {float(v)!r}\n" if i == 6 else f"{n} = {float(v)!r}, {float(v) * 0.1!r}\n")
-    for extra, name in ((["--fresh"], "fresh"), ([], "carry")):
+    for extra, name in ((["--fast"], "fast"), (["--fresh"], "fresh"), ([], "carry")):
         t = time.perf_counter()
         r = subprocess.run(["timeout", "900", CLI, "-i", csv, "-b", pf, "-c", cfg, "-m", "-p", "-o", str(tmp / name)] + extra,
                            capture_output=True, text=True)

@@ -103,6 +103,7 @@ struct ggp_forest {
     int32_t n_partial = 0;
     // streamed upload (ggp_forest_upload_series): chunked copies on their own stream, one event per chunk
     cudaStream_t copy_stream = nullptr;
+    cudaEvent_t pass_done[3] = {nullptr, nullptr, nullptr};   // ggp_predict: forward / backward / combined output complete
     std::vector<cudaEvent_t> chunk_ready;
     cudaEvent_t compute_done = nullptr;
     // streamed evaluation: chunk k's launches run on chunk_stream[k] (the last chunk on the handle's stream), so that the
@@ -384,6 +385,7 @@ int ggp_forest_create(const ggp_forest_desc* d, ggp_forest** out) {
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     if (e == cudaSuccess) e = build_dt_table(f, d->time);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&f->copy_stream, cudaStreamNonBlocking);
+    for (int o = 0; o < 3 && e == cudaSuccess; ++o) e = cudaEventCreateWithFlags(&f->pass_done[o], cudaEventDisableTiming);
     f->chunk_ready.assign(L.n_chunks, nullptr);
     f->timeline = getenv("GGP_B200_TIMELINE") != nullptr;
     for (int k = 0; k < L.n_chunks && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&f->chunk_ready[k], f->timeline ? cudaEventDefault : cudaEventDisableTiming);
@@ -439,6 +441,7 @@ void ggp_forest_destroy(ggp_forest* f) {
     for (cudaEvent_t ev : f->tl_end) if (ev) cudaEventDestroy(ev);
     for (cudaStream_t st : f->chunk_stream) if (st) cudaStreamDestroy(st);
     if (f->copy_stream) cudaStreamDestroy(f->copy_stream);
+    for (cudaEvent_t ev : f->pass_done) if (ev) cudaEventDestroy(ev);
     if (f->ev0) cudaEventDestroy(f->ev0);
     if (f->ev1) cudaEventDestroy(f->ev1);
     delete f;
@@ -885,6 +888,29 @@ int predict_impl(ggp_forest* f, const double* params, int32_t n_seg, double* out
     f->have_prep = false;
     f->last_launches = 0;
     const GgpDevForest F = f->dev();
+    // an output leaves for the host as soon as its pass has finished, on the copy stream, while the next pass runs (the copies
+    // are 6 x the kernels on configs[2]); pack14: 30 % fewer bytes across PCIe, packed on the device into one staging buffer per output
+    const double* src[3] = {f->fwd.p, f->bwd.p, f->comb.p};
+    double* dst[3] = {out_forward, out_backward, out_combined};
+    if (pack14) {
+        int n_out = 0;
+        for (int o = 0; o < 3; ++o) n_out += dst[o] != nullptr;
+        GGP_CUDA(f->pack.ensure((size_t)M * 14 * std::max(n_out, 1)));
+    }
+    int pack_slot = 0;
+    auto ship = [&](int o) -> int {
+        if (!dst[o]) return GGP_OK;
+        GGP_CUDA(cudaEventRecord(f->pass_done[o], s));
+        GGP_CUDA(cudaStreamWaitEvent(f->copy_stream, f->pass_done[o], 0));
+        if (pack14) {
+            double* stage = f->pack.p + (size_t)M * 14 * pack_slot++;
+            ggp_pack14_kernel<<<(unsigned)((M * 14 + 255) / 256), 256, 0, f->copy_stream>>>(M, src[o], stage);
+            GGP_CUDA(cudaMemcpyAsync(dst[o], stage, (size_t)M * 14 * sizeof(double), cudaMemcpyDeviceToHost, f->copy_stream));
+        } else {
+            GGP_CUDA(cudaMemcpyAsync(dst[o], src[o], (size_t)M * 20 * sizeof(double), cudaMemcpyDeviceToHost, f->copy_stream));
+        }
+        return GGP_OK;
+    };
     GGP_CUDA(cudaEventRecord(f->ev0, s));
     for (int g = 0; g < f->n_gen; ++g) {
         GgpFwdArgs A{};
@@ -907,6 +933,7 @@ int predict_impl(ggp_forest* f, const double* params, int32_t n_seg, double* out
             ggp_loglik_coop_kernel<1, false, false, true><<<dim3(ng, 1), GGP_COOP_BLOCK(1), GGP_COOP_SMEM_BYTES(1), s>>>(F, A);
         ++f->last_launches;
     }
+    if (int rc = ship(0)) return rc;
     for (int g = f->n_gen - 1; g >= 0; --g) {
         GgpBwdArgs B{};
         B.slot0 = (int)f->L.gen_start[g];
@@ -927,30 +954,13 @@ int predict_impl(ggp_forest* f, const double* params, int32_t n_seg, double* out
             ggp_backward_coop_kernel<1, false><<<ng, GGP_COOP_BLOCK(1), GGP_COOP_SMEM_BYTES(1), s>>>(F, B);
         ++f->last_launches;
     }
+    if (int rc = ship(1)) return rc;
     ggp_combine_kernel<<<grid_of(M), GGP_BLOCK, 0, s>>>(M, f->fwd.p, f->bwd.p, f->comb_seg.p, f->pred_params.p, f->comb.p);
     ++f->last_launches;
     GGP_CUDA(cudaGetLastError());
     GGP_CUDA(cudaEventRecord(f->ev1, s));
-    if (pack14) {   // 30 % fewer bytes across PCIe: packed on the device, one staging buffer per output so that the copies overlap
-        const size_t bytes = (size_t)M * 14 * sizeof(double);
-        const double* src[3] = {f->fwd.p, f->bwd.p, f->comb.p};
-        double* dst[3] = {out_forward, out_backward, out_combined};
-        int n_out = 0;
-        for (int o = 0; o < 3; ++o) n_out += dst[o] != nullptr;
-        GGP_CUDA(f->pack.ensure((size_t)M * 14 * std::max(n_out, 1)));
-        int slot = 0;
-        for (int o = 0; o < 3; ++o) {
-            if (!dst[o]) continue;
-            double* stage = f->pack.p + (size_t)M * 14 * slot++;
-            ggp_pack14_kernel<<<(unsigned)((M * 14 + 255) / 256), 256, 0, s>>>(M, src[o], stage);
-            GGP_CUDA(cudaMemcpyAsync(dst[o], stage, bytes, cudaMemcpyDeviceToHost, s));
-        }
-    } else {
-        const size_t bytes = (size_t)M * 20 * sizeof(double);
-        if (out_forward) GGP_CUDA(cudaMemcpyAsync(out_forward, f->fwd.p, bytes, cudaMemcpyDeviceToHost, s));
-        if (out_backward) GGP_CUDA(cudaMemcpyAsync(out_backward, f->bwd.p, bytes, cudaMemcpyDeviceToHost, s));
-        if (out_combined) GGP_CUDA(cudaMemcpyAsync(out_combined, f->comb.p, bytes, cudaMemcpyDeviceToHost, s));
-    }
+    if (int rc = ship(2)) return rc;
+    GGP_CUDA(cudaStreamSynchronize(f->copy_stream));
     GGP_CUDA(cudaStreamSynchronize(s));
     float ms = 0.f;
     GGP_CUDA(cudaEventElapsedTime(&ms, f->ev0, f->ev1));

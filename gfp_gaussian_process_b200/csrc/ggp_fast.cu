@@ -8,6 +8,7 @@
 // GGP_FAST_SMEM_DT entries are staged in shared memory, larger ones are read through L1.
 //
 // Build: nvcc -std=c++17 -O3 -fmad=true -gencode arch=compute_100a,code=sm_100a -lineinfo -c
+#include <cstdlib>
 #include "ggp_fast_api.h"
 #include "ggp_fast.cuh"
 
@@ -26,22 +27,36 @@ __global__ void __launch_bounds__(128) ggp_fast_consts_kernel(const GgpFwdArgs A
     ktab[i] = K;
 }
 
-template <int N>
+template <int N, bool ONE>
 struct GgpFastConstsTable {
     const GgpFastConsts<double, N>* tab;   // this vector's entries
     const uint16_t* __restrict__ idx;
-    __device__ __forceinline__ const GgpFastConsts<double, N>& at(int64_t k, int64_t) const { return tab[idx[k]]; }
+    // ONE: the forest has a single distinct time step (a fixed acquisition interval): no index to read.  The zero comes out of
+    // an opaque instruction: with a literal the compiler hoists the entry's 16 + 16 N loads out of the step loop (1.5 kB of spills)
+    __device__ __forceinline__ const GgpFastConsts<double, N>& at(int64_t k, int64_t) const {
+        if (ONE) {
+            int z;
+            asm volatile("mov.s32 %0, 0;" : "=r"(z));
+            return tab[z];
+        }
+        // (reading the index one step ahead - a register across the step, or across the measurement update only - was measured
+        // slower: 0.67 / 0.63 vs 0.61 ms; at 168 registers the extra live value is spilled right behind its load)
+        return tab[idx[k]];
+    }
 };
 
 // MB = blocks resident per SM the register allocation is made for (2: ~250 registers, 3: 168, 4: 128; measured)
-// SMEM: the constants table fits the block's shared copy (n_dt <= GGP_FAST_SMEM_DT): shared-memory loads with known address space
-template <int N, int MB, bool SMEM>
+// TAB 0: the constants table is read through L1; 1: it fits the block's shared copy (n_dt <= GGP_FAST_SMEM_DT): shared-memory loads
+// with known address space; 2: one entry (n_dt == 1), shared, and the per-point index is not read at all (its load was the
+// kernel's one exposed memory latency: the table address of a step depends on it)
+template <int N, int MB, int TAB>
 __global__ void __launch_bounds__(GGP_FAST_BLOCK, MB) ggp_fast_loglik_kernel(const GgpDevForest F, const GgpFwdArgs A,
                                                                         const GgpFastConsts<double, N>* __restrict__ ktab,
                                                                         int* __restrict__ invalid) {
     __shared__ double sp[GGP_NP];
     __shared__ double red[GGP_FAST_BLOCK / 32];
-    __shared__ GgpFastConsts<double, N> ks[SMEM ? GGP_FAST_SMEM_DT : 1];
+    constexpr bool SMEM = TAB != 0;
+    __shared__ GgpFastConsts<double, N> ks[TAB == 1 ? GGP_FAST_SMEM_DT : 1];
     const int lane_slot = blockIdx.x * GGP_FAST_BLOCK + threadIdx.x;
     const bool active = lane_slot < A.n_slots;
     const int slot = A.slot0 + (active ? lane_slot : 0);
@@ -67,7 +82,7 @@ __global__ void __launch_bounds__(GGP_FAST_BLOCK, MB) ggp_fast_loglik_kernel(con
 #pragma unroll
             for (int k = 0; k < 10; ++k) s.c[k] = A.state[(4 + k) * vstride + vbase + parent];
         }
-        GgpFastConstsTable<N> kp{SMEM ? ks : kv, F.dt_idx};
+        GgpFastConstsTable<N, TAB == 2> kp{SMEM ? ks : kv, F.dt_idx};
         bool valid = true;
         own = ggp_fast_cell<double, N>(F, slot, sp, s, kp, valid);
         if (F.s_d1[slot] >= 0 || F.s_d2[slot] >= 0) {
@@ -124,15 +139,19 @@ cudaError_t ggp_fast_consts_launch(const GgpFwdArgs& A, const double* dt_values,
 cudaError_t ggp_fast_loglik_launch(const GgpDevForest& F, const GgpFwdArgs& A, const void* ktab, int* invalid, int n_nodes,
                                    int blocks_per_sm, cudaStream_t stream) {
     const dim3 grid((unsigned)((A.n_slots + GGP_FAST_BLOCK - 1) / GGP_FAST_BLOCK), (unsigned)A.v_count);
-    const bool smem = F.n_dt <= GGP_FAST_SMEM_DT;
-#define GGP_FAST_LAUNCH(MBV, SM) GGP_FAST_DISPATCH(n_nodes, (ggp_fast_loglik_kernel<NN, MBV, SM><<<grid, GGP_FAST_BLOCK, 0, stream>>>(F, A, static_cast<const GgpFastConsts<double, NN>*>(ktab), invalid)))
+    int tab = F.n_dt == 1 ? 2 : (F.n_dt <= GGP_FAST_SMEM_DT ? 1 : 0);
+    static const int tab_force = [] { const char* m = getenv("GGP_B200_FAST_TAB"); return m ? atoi(m) : -1; }();   // A/B runs: 0 or 1
+    if (tab_force == 0 || (tab_force == 1 && tab == 2)) tab = tab_force;
+#define GGP_FAST_LAUNCH(MBV, TB) GGP_FAST_DISPATCH(n_nodes, (ggp_fast_loglik_kernel<NN, MBV, TB><<<grid, GGP_FAST_BLOCK, 0, stream>>>(F, A, static_cast<const GgpFastConsts<double, NN>*>(ktab), invalid)))
+#define GGP_FAST_LAUNCH_TAB(MBV) if (tab == 2) { GGP_FAST_LAUNCH(MBV, 2) } else if (tab == 1) { GGP_FAST_LAUNCH(MBV, 1) } else { GGP_FAST_LAUNCH(MBV, 0) }
     if (blocks_per_sm <= 2) {
-        if (smem) { GGP_FAST_LAUNCH(2, true) } else { GGP_FAST_LAUNCH(2, false) }
+        GGP_FAST_LAUNCH_TAB(2)
     } else if (blocks_per_sm == 3) {
-        if (smem) { GGP_FAST_LAUNCH(3, true) } else { GGP_FAST_LAUNCH(3, false) }
+        GGP_FAST_LAUNCH_TAB(3)
     } else {
-        if (smem) { GGP_FAST_LAUNCH(4, true) } else { GGP_FAST_LAUNCH(4, false) }
+        GGP_FAST_LAUNCH_TAB(4)
     }
+#undef GGP_FAST_LAUNCH_TAB
 #undef GGP_FAST_LAUNCH
     return cudaGetLastError();
 }

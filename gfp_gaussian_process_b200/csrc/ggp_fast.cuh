@@ -62,26 +62,25 @@ template <> struct GgpFx<double> {
     static GGP_HDM double abs_(double x) { return fabs(x); }
     static GGP_HDM bool finite_(double x) { return x - x == 0.0; }
     static GGP_HDM double ln2() { return 0.6931471805599453; }
-    // exp(x) for |x| <= 0.125: degree-10 Taylor polynomial, truncation 0.125^11 / 11! = 3e-18 relative
-    static GGP_HDM double exp_small_(double x) {
-        double p = ggp_fexp_k(0);
+    // Taylor polynomial of exp of degree DEG (4 .. 10), Horner; relative truncation error |x|^(DEG+1) / (DEG+1)!
+    template <int DEG>
+    static GGP_HDM double exp_taylor_(double x) {
+        double p = ggp_fexp_k(10 - DEG);
 #pragma unroll
-        for (int i = 1; i < 9; ++i) p = p * x + ggp_fexp_k(i);
+        for (int i = 11 - DEG; i < 9; ++i) p = p * x + ggp_fexp_k(i);
         p = p * x + 1.0;
         return p * x + 1.0;
     }
-    // exp(x) for |x| <= 0.01: degree 6, truncation 0.01^7 / 7! = 2e-18 relative
-    static GGP_HDM double exp_tiny_(double x) {
-        double p = ggp_fexp_k(4);
-#pragma unroll
-        for (int i = 5; i < 9; ++i) p = p * x + ggp_fexp_k(i);
-        p = p * x + 1.0;
-        return p * x + 1.0;
-    }
+    static GGP_HDM double exp_small_(double x) { return exp_taylor_<10>(x); }   // |x| <= 0.125: 3e-18
+    static GGP_HDM double exp_small8_(double x) { return exp_taylor_<8>(x); }   // |x| <= 0.06: 3e-17
+    static GGP_HDM double exp_tiny_(double x) { return exp_taylor_<6>(x); }     // |x| <= 0.01: 2e-18
+    static GGP_HDM double exp_tiny4_(double x) { return exp_taylor_<4>(x); }    // |x| <= 0.001: 8e-18
 };
-// range of exp_small_ / exp_tiny_
+// ranges of exp_small_ / exp_small8_ / exp_tiny_ / exp_tiny4_
 #define GGP_FAST_SMALL 0.125
+#define GGP_FAST_SMALL8 0.06
 #define GGP_FAST_TINY 0.01
+#define GGP_FAST_TINY4 0.001
 
 // largest |d(exponent)/ds| * t a step may have for the N-node rule to integrate s^k exp(lambda s), k = 0..3, over [0, t] and
 // [t, 2t] to 3e-15 relative (measured against mpmath)
@@ -167,10 +166,11 @@ GGP_HD void ggp_fast_consts(GgpFastConsts<T, N>& K, T t, T ml, T gl, T sl2, T mq
     }
 }
 
-// the quadrature sums of one step.  TINY: the two secondary exponents (Cxl s and 2 a t s) stay below 0.01 and the main one
-// (a s^2 + B0 s) below 0.125 over the step: all three exponentials of a node are short polynomials; else the library's exp.
-// Every sum is one FMA per node against a pre-multiplied constant.
-template <class T, int N, bool TINY>
+// the quadrature sums of one step.  LEVEL 1: the two secondary exponents (Cxl s and 2 a t s) stay below 0.01 and the main one
+// (a s^2 + B0 s) below 0.125 over the step: all three exponentials of a node are short polynomials (degrees 6 and 10); LEVEL 2:
+// below 0.001 and 0.06, degrees 4 and 8 (what real data sets and configs[1] have: growth rates of 1e-2 per minute, steps of
+// minutes); LEVEL 0: the library's exp.  Every sum is one FMA per node against a pre-multiplied constant.
+template <class T, int N, int LEVEL>
 GGP_HD void ggp_fast_moments(const GgpFastConsts<T, N>& K, T a, T B0, T Cxl, T EH, T* __restrict__ M) {
     typedef GgpFx<T> X;
     const T t = K.t, twoat = T(2) * a * t;
@@ -181,9 +181,10 @@ GGP_HD void ggp_fast_moments(const GgpFastConsts<T, N>& K, T a, T B0, T Cxl, T E
     for (int j = 0; j < N; ++j) {
         const GgpFastNode<T> n = K.node[j];
         const T s = n.s;
-        const T A = TINY ? X::exp_small_(a * n.s2 + B0 * s) : X::exp_(a * n.s2 + B0 * s);   // exp(a s^2 + B0 s)
-        const T V = TINY ? X::exp_tiny_(Cxl * s) : X::exp_(Cxl * s);
-        const T U = TINY ? X::exp_tiny_(twoat * s) : X::exp_(twoat * s);
+        const T xa = a * n.s2 + B0 * s, xv = Cxl * s, xu = twoat * s;
+        const T A = LEVEL == 2 ? X::exp_small8_(xa) : LEVEL == 1 ? X::exp_small_(xa) : X::exp_(xa);   // exp(a s^2 + B0 s)
+        const T V = LEVEL == 2 ? X::exp_tiny4_(xv) : LEVEL == 1 ? X::exp_tiny_(xv) : X::exp_(xv);
+        const T U = LEVEL == 2 ? X::exp_tiny4_(xu) : LEVEL == 1 ? X::exp_tiny_(xu) : X::exp_(xu);
         const T AW = A * V;                                    // exp(a s^2 + W s), W = B0 + Cxl
         const T H = AW * (U * EH);                             // exp(a s'^2 + W s'), s' = t + s, EH = exp(t (W + a t))
         MB0 += n.w * A; MB1 += n.ws * A;
@@ -220,14 +221,20 @@ GGP_HD bool ggp_fast_propagate(GgpFastState<T>& st, const GgpFastConsts<T, N>& K
     // these exponentials are short polynomials as well
     const T sec = X::abs_(Cxl) > T(2) * a * t ? X::abs_(Cxl) : T(2) * a * t;
     const bool small = lam * t <= T(GGP_FAST_SMALL);
-    const T EH = small ? X::exp_small_(t * (W + a * t)) : X::exp_(t * (W + a * t));
+    // the exponents the polynomials see: |a s^2 + B s| <= (|B| + |a| t) t on [0, t] and |t (W + a t)| (gq lives in the weights)
+    const T xmain = ((X::abs_(B0) > X::abs_(W) ? X::abs_(B0) : X::abs_(W)) + X::abs_(a) * t) * t;
+    const int level = !small ? 0 : (xmain <= T(GGP_FAST_SMALL8) && sec * t <= T(GGP_FAST_TINY4)) ? 2 : (sec * t <= T(GGP_FAST_TINY) ? 1 : 0);
+    const T xh = t * (W + a * t);
+    const T EH = level == 2 ? X::exp_small8_(xh) : small ? X::exp_small_(xh) : X::exp_(xh);
     T M[19];
-    if (small && sec * t <= T(GGP_FAST_TINY)) ggp_fast_moments<T, N, true>(K, a, B0, Cxl, EH, M);
-    else ggp_fast_moments<T, N, false>(K, a, B0, Cxl, EH, M);
+    if (level == 2) ggp_fast_moments<T, N, 2>(K, a, B0, Cxl, EH, M);
+    else if (level == 1) ggp_fast_moments<T, N, 1>(K, a, B0, Cxl, EH, M);
+    else ggp_fast_moments<T, N, 0>(K, a, B0, Cxl, EH, M);
     // exp(c): c0 = bx + Cxx/2 - b t (B-family, mean_cov_model.h:76-115), c5 = 2 (bx + Cxx - b t) (W-family, :124-164)
     const T E1 = X::exp_(bx + T(0.5) * Cxx);
     const T Ec0 = E1 * K.ebt;
-    const T Ec5 = (E1 * K.ebt) * (E1 * K.ebt) * (X::abs_(Cxx) <= T(GGP_FAST_SMALL) ? X::exp_small_(Cxx) : X::exp_(Cxx));
+    const T aCxx = X::abs_(Cxx);
+    const T Ec5 = (E1 * K.ebt) * (E1 * K.ebt) * (aCxx <= T(GGP_FAST_TINY) ? X::exp_tiny_(Cxx) : aCxx <= T(GGP_FAST_SMALL) ? X::exp_small_(Cxx) : X::exp_(Cxx));
     const T JB0 = Ec0 * M[0], JB1 = Ec0 * M[1];                        // I_k(B0, c0; 0, t)
     const T JBm0 = Ec0 * M[2], JBm1 = Ec0 * M[3], JBm2 = Ec0 * M[4];   // I_k(B0 - gq, c0; 0, t)
     const T JBs0 = Ec0 * M[5];                                         // I_0(B0 + gq, c0) - I_0(B0 - gq, c0)

@@ -15,7 +15,9 @@ typedef __float128 quad;
 template <> struct GgpFx<quad> {
     static quad exp_(quad x) { return expq(x); }
     static quad exp_small_(quad x) { return expq(x); }
+    static quad exp_small8_(quad x) { return expq(x); }
     static quad exp_tiny_(quad x) { return expq(x); }
+    static quad exp_tiny4_(quad x) { return expq(x); }
     static quad log_(quad x) { return logq(x); }
     static quad expm1_(quad x) { return expm1q(x); }
     static quad abs_(quad x) { return fabsq(x); }

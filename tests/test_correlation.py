@@ -150,3 +150,46 @@ def test_correlation_sums_at_config4_size():
     assert np.array_equal(np.asarray(sums[:, 0], dtype=np.int64), want)
     assert np.isfinite(np.asarray(sums, dtype=np.float64)).all()
     f.close()
+
+
+@pytest.mark.gpu
+def test_correlation_sums_take_any_number_of_lag_bins_and_repeat():
+    """the accumulators live in global memory (lock-free compensated sums): more lag bins than the 256 the first version's
+    shared-memory bins held; the sums of the leading bins do not depend on the number of bins; two runs agree although
+    the order of the atomic additions differs (the error words make the totals exact to second order)"""
+    import gfp_gaussian_process_b200 as ggp
+    P = ggp.PARAMS_SCALED_BINOMIAL
+    d = ggp.simulate_forest(12, 5, params=P, noise_model="scaled", division_model="binomial", seed=5, pts_range=(6, 11))
+    f = ggp.Forest(d)
+    ggp.prediction_forward_backward(f, [P], forward=False, backward=False, combined=False)
+    dt = float(d.time[1] - d.time[0])
+    s40, n40 = ggp.api.correlation_sums(f, [P], dt, 40)
+    s600, n600 = ggp.api.correlation_sums(f, [P], dt, 600)
+    s600b, _ = ggp.api.correlation_sums(f, [P], dt, 600)
+    assert n40 == n600 == ggp.count_joints(f, [P], 1e-10) > 0
+    assert np.array_equal(s600[:, 0], s600b[:, 0]) and np.array_equal(s40[:, 0], s600[:40, 0])
+    assert s600[:, 0].sum() > s40[:, 0].sum() or s600[40:, 0].sum() == 0      # deeper lags exist only beyond bin 40
+    a, b, c = (np.asarray(x, dtype=np.float64) for x in (s40, s600[:40], s600b[:40]))
+    assert np.allclose(a, b, rtol=1e-14, atol=1e-300) and np.allclose(b, c, rtol=1e-14, atol=1e-300)
+    assert np.all(s600[int(s600[:, 0].nonzero()[0].max()) + 1:] == 0)
+    f.close()
+
+
+@pytest.mark.gpu
+def test_joints_into_preallocated_arrays():
+    """collect_joint_distributions(out=...) fills the caller's (e.g. pinned) arrays with the same records"""
+    import gfp_gaussian_process_b200 as ggp
+    P = ggp.PARAMS_CONST_GAUSS
+    d = ggp.simulate_forest(5, 4, seed=3, pts_range=(5, 8))
+    f = ggp.Forest(d)
+    ggp.prediction_forward_backward(f, [P], forward=False, backward=False, combined=False)
+    r, c, m, v = ggp.collect_joint_distributions(f, [P], 1e-10)
+    n = len(r)
+    out = (np.full(n + 7, -1, dtype=np.int64), np.full(n + 7, -1, dtype=np.int64), np.full((n + 7, 44), np.nan))
+    r2, c2, m2, v2 = ggp.collect_joint_distributions(f, [P], 1e-10, out=out)
+    assert len(r2) == n and np.array_equal(r, r2) and np.array_equal(c, c2)
+    assert np.array_equal(m.view(np.uint64), m2.view(np.uint64)) and np.array_equal(v.view(np.uint64), v2.view(np.uint64))
+    assert np.all(out[0][n:] == -1)
+    with pytest.raises(ValueError):
+        ggp.collect_joint_distributions(f, [P], 1e-10, out=(out[0], out[1], np.zeros((n, 43))))
+    f.close()

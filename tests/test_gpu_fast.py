@@ -117,3 +117,30 @@ def test_fast_falls_back_to_strict_outside_its_validity_range():
     f.set_mode("strict")
     assert rel(ll_w, ggp.total_likelihood(wide, f)) <= GATE
     f.close()
+
+
+@pytest.mark.parametrize("grid", ["two_steps", "many_steps"])
+def test_fast_gate_on_irregular_time_grids(grid):
+    """the constants' table of the fast kernels: 2 distinct time steps (table in shared memory, per-point index) and hundreds
+    (table read through L1); a uniform grid takes the index-free path (every other test).  Random parameter vectors around the
+    example's values: the gate against the strict kernels (== oracle per cell), and against the oracle itself for the first"""
+    P = ggp.PARAMS_SCALED_BINOMIAL
+    d = ggp.simulate_forest(40, 4, params=P, noise_model="scaled", division_model="binomial", seed=77, dt=6.0)
+    k = np.rint(d.time / 6.0)
+    if grid == "two_steps":
+        d.time = 6.0 * k + np.where(k % 2 == 1, 1.5, 0.0)          # steps of 7.5 and 4.5
+    else:
+        d.time = 6.0 * k + 1.7 * np.sin(k * 0.37)                   # every step different
+    rng = np.random.default_rng(11)
+    vecs = P * np.exp(rng.uniform(-0.4, 0.4, size=(12, 11)))
+    vecs[0] = P
+    f = ggp.Forest(d)
+    strict = ggp.total_likelihood(vecs, f, raise_on_nan=False)
+    f.set_mode("fast")
+    fast = ggp.total_likelihood(vecs, f, raise_on_nan=False)
+    ok = np.isfinite(strict)
+    assert ok.sum() >= 10 and np.array_equal(np.isfinite(fast), ok)
+    assert np.max(np.abs(fast[ok] - strict[ok]) / np.abs(strict[ok])) <= GATE
+    assert f.last_strict_reruns <= 2 and np.any(fast[ok] != strict[ok])
+    assert rel(fast[0], Oracle(d).total_loglik(vecs[0])) <= GATE
+    f.close()

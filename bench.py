@@ -357,6 +357,21 @@ def run_ours(args):
         torch.cuda.synchronize()
         return allmax((time.perf_counter() - t0) / steps), allsum(ll)
 
+    # the end-to-end step's roofline: the same two pinned arrays copied to the device with nothing else going on (PCIe alone)
+    def timed_pcie_copy(reps):
+        dev = [torch.empty(a.shape, dtype=a.dtype, device="cuda") for a in pin]
+        ts = []
+        for _ in range(reps + 1):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for dst, src in zip(dev, pin):
+                dst.copy_(src, non_blocking=True)
+            torch.cuda.synchronize()
+            ts.append(time.perf_counter() - t0)
+        return allmax(float(np.median(ts[1:])))
+
+    pcie_copy_s = timed_pcie_copy(5)
+
     res = {}
     for mode in ("strict", "fast"):
         forest.set_mode(mode)
@@ -447,6 +462,11 @@ def run_ours(args):
             r = res[mode]
             return {"value": ctp_total / r["e2e_s"], "unit": "ctp/s", "h2d_bytes_per_step": int(2 * 8 * n_ctp + 88 + 64),
                     "d2h_bytes_per_step": 16, "ms_per_step": r["e2e_s"] * 1e3,
+                    "h2d_gbps_per_gpu": 2 * 8 * n_ctp / r["e2e_s"] / 1e9,
+                    "pcie": {"copy_alone_ms": pcie_copy_s * 1e3, "copy_alone_gbps_per_gpu": 2 * 8 * n_ctp / pcie_copy_s / 1e9,
+                             "frac": pcie_copy_s / r["e2e_s"],
+                             "what": "the step's two pinned arrays copied to the device with nothing else running (max over ranks): "
+                                     "the end-to-end step is bound by this link, frac = copy alone / whole step"},
                     "what": "ggp_forest_upload_series (this step's log_length and fp from pinned host memory with their init_cells "
                             "statistics; the unchanged time grid is not sent again) + ggp_loglik (host params in, host log-likelihood "
                             "and NaN record out), wall clock around the host calls"}

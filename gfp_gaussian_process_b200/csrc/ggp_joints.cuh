@@ -407,8 +407,14 @@ GGP_HD void ggp_emit_joint(const GgpJointArgs& A, int64_t row, int64_t col, cons
     const unsigned long long idx = (*A.count)++;
 #endif
     if ((long long)idx >= A.cap) return;
+#if defined(__CUDA_ARCH__)
+    // streaming stores: a walker keeps ~600 bytes of spilled state in L1, records are written once and read by another kernel
+    __stcs(A.row_ctp + idx, (long long)row);
+    __stcs(A.col_ctp + idx, (long long)col);
+#else
     A.row_ctp[idx] = row;
     A.col_ctp[idx] = col;
+#endif
     double* r = A.rec44 + 44 * idx;
     double v[44];
 #pragma unroll
@@ -422,7 +428,7 @@ GGP_HD void ggp_emit_joint(const GgpJointArgs& A, int64_t row, int64_t col, cons
     // a record is 352 bytes at a multiple of 352 from a 256-byte aligned base: 22 sixteen-byte stores instead of 44 eight-byte ones
     double2* r2 = reinterpret_cast<double2*>(r);
 #pragma unroll
-    for (int i = 0; i < 22; ++i) r2[i] = make_double2(v[2 * i], v[2 * i + 1]);
+    for (int i = 0; i < 22; ++i) __stcs(r2 + i, make_double2(v[2 * i], v[2 * i + 1]));
 #else
     for (int i = 0; i < 44; ++i) r[i] = v[i];
 #endif

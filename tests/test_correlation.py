@@ -153,7 +153,7 @@ def test_correlation_sums_at_config4_size():
 
 
 @pytest.mark.gpu
-def test_correlation_sums_take_any_number_of_lag_bins_and_repeat():
+def test_correlation_sums_take_any_number_of_lag_bins_and_repeat(monkeypatch):
     """the accumulators live in global memory (lock-free compensated sums): more lag bins than the 256 the first version's
     shared-memory bins held; the sums of the leading bins do not depend on the number of bins; two runs agree although
     the order of the atomic additions differs (the error words make the totals exact to second order)"""
@@ -172,6 +172,12 @@ def test_correlation_sums_take_any_number_of_lag_bins_and_repeat():
     a, b, c = (np.asarray(x, dtype=np.float64) for x in (s40, s600[:40], s600b[:40]))
     assert np.allclose(a, b, rtol=1e-14, atol=1e-300) and np.allclose(b, c, rtol=1e-14, atol=1e-300)
     assert np.all(s600[int(s600[:, 0].nonzero()[0].max()) + 1:] == 0)
+    # a record budget of 1 MB (2 600 records): many row blocks, and blocks that overflow their buffers are halved and walked again
+    monkeypatch.setenv("GGP_B200_CORR_BUDGET", str(1 << 20))
+    s_small, n_small = ggp.api.correlation_sums(f, [P], dt, 600)
+    monkeypatch.delenv("GGP_B200_CORR_BUDGET")
+    assert n_small == n600 and np.array_equal(s_small[:, 0], s600[:, 0])
+    assert np.allclose(np.asarray(s_small, dtype=np.float64), np.asarray(s600, dtype=np.float64), rtol=1e-14, atol=1e-300)
     f.close()
 
 

@@ -1049,23 +1049,21 @@ int ggp_fp64_peak(int32_t device, double* tflops_out) {
     GGP_CUDA(cudaGetDeviceProperties(&prop, device));
     DevBuf<double> out;
     GGP_CUDA(out.ensure(1));
-    cudaEvent_t e0, e1;
-    GGP_CUDA(cudaEventCreate(&e0));
-    GGP_CUDA(cudaEventCreate(&e1));
+    ScopedEvent e0, e1;   // destroyed on every return path
+    GGP_CUDA(e0.create());
+    GGP_CUDA(e1.create());
     const int blocks = prop.multiProcessorCount * 8, iters = 1 << 15;
     double best = 0.0;
     for (int rep = 0; rep < 6; ++rep) {
-        GGP_CUDA(cudaEventRecord(e0));
+        GGP_CUDA(cudaEventRecord(e0.ev));
         ggp_fp64_peak_kernel<<<blocks, 256>>>(iters, 0.999999, 1e-9, out.p);
-        GGP_CUDA(cudaEventRecord(e1));
-        GGP_CUDA(cudaEventSynchronize(e1));
+        GGP_CUDA(cudaEventRecord(e1.ev));
+        GGP_CUDA(cudaEventSynchronize(e1.ev));
         float ms = 0.f;
-        GGP_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        GGP_CUDA(cudaEventElapsedTime(&ms, e0.ev, e1.ev));
         const double tf = 2.0 * 8.0 * (double)iters * 256.0 * blocks / (ms * 1e-3) / 1e12;
         if (rep > 0 && tf > best) best = tf;
     }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     out.release();
     *tflops_out = best;
     return GGP_OK;

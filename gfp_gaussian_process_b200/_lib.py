@@ -68,6 +68,10 @@ SIGNATURES = {
     "ggp_group_loglik": (C.c_int, [C.c_void_p, c_double_p, C.c_int32, c_double_p, c_double_p, c_double_p, C.POINTER(NanInfo)]),
     "ggp_group_predict": (C.c_int, [C.c_void_p, c_double_p, C.c_int32, c_double_p, c_double_p, c_double_p]),
     "ggp_group_predict14": (C.c_int, [C.c_void_p, c_double_p, C.c_int32, c_double_p, c_double_p, c_double_p]),
+    "ggp_group_joints": (C.c_int, [C.c_void_p, c_double_p, C.c_int32, C.c_double, C.c_int64, C.c_int64, C.c_int64, c_int64_p,
+                                   c_int64_p, c_int64_p, c_double_p]),
+    "ggp_group_correlation_sums": (C.c_int, [C.c_void_p, c_double_p, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_double, C.c_int32,
+                                             c_double_p, c_double_p, c_int64_p]),
     "ggp_forest_set_mode": (C.c_int, [C.c_void_p, C.c_int32]),
     "ggp_forest_get_mode": (C.c_int32, [C.c_void_p]),
     "ggp_last_fast_nodes": (C.c_int32, [C.c_void_p]),

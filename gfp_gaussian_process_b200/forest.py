@@ -312,3 +312,28 @@ class ForestGroup:
         _lib.check(fn(self._h, p.ctypes.data_as(_lib.c_double_p), p.shape[0], *[bufs[k].ctypes.data_as(_lib.c_double_p) if k in bufs else None
                                                                                for k in ("forward", "backward", "prediction")]))
         return bufs
+
+    def joints(self, params_vecs, tolerance_joint=1e-10, row_begin=0, row_end=None):
+        """collect_joint_distributions over the shards (ggp_group_joints): (row_ctp, col_ctp, mean [n][8], cov_upper [n][36]) in the
+        caller's time-point indices, sorted by (row, col); predictions() must have run with the same params_vecs"""
+        p = np.ascontiguousarray(params_vecs, dtype=np.float64).reshape(-1, _lib.N_PARAMS)
+        row_end = self.n_ctp if row_end is None else row_end
+        cnt = C.c_int64(0)
+        args = (self._h, p.ctypes.data_as(_lib.c_double_p), p.shape[0], C.c_double(tolerance_joint), row_begin, row_end)
+        _lib.check(self._lib.ggp_group_joints(*args, 0, C.byref(cnt), None, None, None))
+        n = cnt.value
+        row, col, rec = np.empty(max(n, 1), dtype=np.int64), np.empty(max(n, 1), dtype=np.int64), np.empty((max(n, 1), 44))
+        _lib.check(self._lib.ggp_group_joints(*args, n, C.byref(cnt), row.ctypes.data_as(_lib.c_int64_p), col.ctypes.data_as(_lib.c_int64_p),
+                                              rec.ctypes.data_as(_lib.c_double_p)))
+        return row[:n], col[:n], rec[:n, :8], rec[:n, 8:]
+
+    def correlation_sums(self, params_vecs, dt_step, n_bins, tolerance_joint=1e-10, atol=None, normalize_time=False):
+        """lag-binned moment sums of the correlation functions over all shards (ggp_group_correlation_sums)"""
+        p = np.ascontiguousarray(params_vecs, dtype=np.float64).reshape(-1, _lib.N_PARAMS)
+        hi, lo = np.zeros((n_bins, 50)), np.zeros((n_bins, 50))
+        nj = C.c_int64(0)
+        _lib.check(self._lib.ggp_group_correlation_sums(self._h, p.ctypes.data_as(_lib.c_double_p), p.shape[0], C.c_double(tolerance_joint),
+                                                        C.c_double(dt_step), n_bins, C.c_double(0.2 * dt_step if atol is None else atol),
+                                                        1 if normalize_time else 0, hi.ctypes.data_as(_lib.c_double_p),
+                                                        lo.ctypes.data_as(_lib.c_double_p), C.byref(nj)))
+        return hi.astype(np.longdouble) + lo.astype(np.longdouble), nj.value

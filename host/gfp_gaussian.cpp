@@ -13,8 +13,8 @@
 //     batched launches; results are those of one-by-one evaluation (the library chains the reference's history
 //     dependence, SURVEY.md H3, through `root_carry` in evaluation order);
 //   * NLopt is replaced by ggp_neldermead.hpp (iterate parity unpinned);
-//   * extra options: --device N, --devices a,b,.. (lineage trees sharded over several GPUs, one host thread and one
-//     forest handle each; the scalar log-likelihoods are added on the host, predictions gathered by ctp), --fresh (every evaluation starts from zero root off-diagonals, i.e. is a pure
+//   * extra options: --device N, --devices a,b,.. (lineage trees sharded over several GPUs behind one library handle, ggp_group:
+//     likelihood, predictions, joints and correlation sums all run on every device), --fresh (every evaluation starts from zero root off-diagonals, i.e. is a pure
 //     function of the parameters; enables speculative batching of the simplex moves), --sparse_joints (one line per
 //     joint instead of the dense matrix whose size is quadratic in the data set).
 #include <cstdio>
@@ -59,7 +59,12 @@ public:
     virtual std::vector<double> loglik(Session& S, const std::vector<std::vector<double>>& P) = 0;
     // combined predictions [n_ctp][20] in the table's ctp order (main.cpp:132-140)
     virtual void predict(const std::vector<double>& P, int n_seg, std::vector<double>& comb) = 0;
-    virtual ggp_forest* joints_handle() = 0;   // a handle that holds the whole table and its predictions, or nullptr
+    // joints of the start points [r0, r1) in (row, col) order and the lag-binned correlation sums, in the table's ctp indices
+    // (ggp_joints / ggp_correlation_sums; predict() with the same parameters comes first).  Return the library's status code.
+    virtual int joints(const std::vector<double>& P, int n_seg, double tol, int64_t r0, int64_t r1, int64_t cap, int64_t* n,
+                       int64_t* row, int64_t* col, double* rec) = 0;
+    virtual int correlation_sums(const std::vector<double>& P, int n_seg, double tol, double step, int n_bins, double atol,
+                                 bool normalize_time, double* hi, double* lo, int64_t* n_joints) = 0;
 };
 
 struct LoglikResult {
@@ -99,7 +104,14 @@ public:
     DeviceForest(const DeviceForest&) = delete;
     ggp_forest* handle() const { return h_; }
     const LineageTable& table() const override { return table_; }
-    ggp_forest* joints_handle() override { return h_; }
+    int joints(const std::vector<double>& P, int n_seg, double tol, int64_t r0, int64_t r1, int64_t cap, int64_t* n, int64_t* row,
+               int64_t* col, double* rec) override {
+        return ggp_joints(h_, P.data(), n_seg, tol, r0, r1, cap, n, row, col, rec);
+    }
+    int correlation_sums(const std::vector<double>& P, int n_seg, double tol, double step, int n_bins, double atol, bool normalize_time,
+                         double* hi, double* lo, int64_t* n_joints) override {
+        return ggp_correlation_sums(h_, P.data(), n_seg, tol, step, n_bins, atol, normalize_time ? 1 : 0, hi, lo, n_joints);
+    }
 
     LoglikResult loglik_raw(const std::vector<double>& flat, int n_vec, bool fresh) {
         LoglikResult R;
@@ -130,126 +142,58 @@ private:
     std::vector<double> carry_;
 };
 
-// The table's trees sharded over several devices: roots are bin-packed by cell-timepoint count, every
-// descendant stays with its root, the init_cells statistics are those of the whole table.  One handle and one host
-// thread per device; the per-shard log-likelihoods are added in shard order, predictions are scattered back by ctp.
-class ShardedForest : public Forest {
+// The table's trees sharded over several devices behind ONE library handle (ggp_group): every descendant
+// stays with its root, the init_cells statistics are those of the whole table, one host thread per device inside a call; the
+// per-shard log-likelihoods are added in shard order, prediction rows, joints and the first NaN come back in the table's order.
+class GroupForest : public Forest {
 public:
-    ShardedForest(const LineageTable& T, const std::vector<int>& devices) : table_(T) {
-        const int64_t N = T.n_cells();
-        const int D = (int)devices.size();
-        // tree of every cell (parents may come after daughters in the file)
-        std::vector<int32_t> root_of(N, -1);
-        for (int64_t c = 0; c < N; ++c) {
-            int64_t u = c;
-            std::vector<int64_t> chain;
-            while (root_of[u] < 0 && T.parent[u] >= 0) { chain.push_back(u); u = T.parent[u]; }
-            const int32_t r = root_of[u] >= 0 ? root_of[u] : (int32_t)u;
-            root_of[u] = r;
-            for (int64_t w : chain) root_of[w] = r;
-        }
-        std::vector<int64_t> size(N, 0);
-        std::vector<int32_t> roots;
-        for (int64_t c = 0; c < N; ++c) {
-            size[root_of[c]] += T.n_points(c);
-            if (T.parent[c] < 0) roots.push_back((int32_t)c);
-        }
-        std::stable_sort(roots.begin(), roots.end(), [&](int32_t a, int32_t b) { return size[a] > size[b]; });
-        std::vector<int64_t> load(D, 0);
-        std::vector<int32_t> shard_of_root(N, 0);
-        for (int32_t r : roots) {
-            const int k = (int)(std::min_element(load.begin(), load.end()) - load.begin());
-            shard_of_root[r] = k;
-            load[k] += size[r];
-        }
-        // sub-tables in file order
-        tables_.resize(D);
-        cells_.resize(D);
-        ctp_.resize(D);
-        std::vector<int32_t> local(N, -1);
-        for (int64_t c = 0; c < N; ++c) {
-            const int k = shard_of_root[root_of[c]];
-            local[c] = (int32_t)cells_[k].size();
-            cells_[k].push_back(c);
-        }
-        for (int k = 0; k < D; ++k) {
-            LineageTable& Sx = tables_[k];
-            Sx.noise_model = T.noise_model; Sx.division_model = T.division_model; Sx.fp_auto = T.fp_auto;
-            auto rm = [&](int32_t c) { return c < 0 ? -1 : local[c]; };
-            for (int64_t c : cells_[k]) {
-                Sx.cell_id.push_back(T.cell_id[c]); Sx.parent_id.push_back(T.parent_id[c]);
-                Sx.parent.push_back(rm(T.parent[c])); Sx.daughter1.push_back(rm(T.daughter1[c])); Sx.daughter2.push_back(rm(T.daughter2[c]));
-                for (int64_t i = T.offset[c]; i < T.offset[c + 1]; ++i) {
-                    Sx.time.push_back(T.time[i]); Sx.log_length.push_back(T.log_length[i]); Sx.fp.push_back(T.fp[i]);
-                    Sx.segment.push_back(T.segment[i]);
-                    ctp_[k].push_back(i);
-                }
-                Sx.offset.push_back((int64_t)Sx.time.size());
-            }
-        }
-        double init_f[4], init_r[4];
-        const ggp_forest_desc whole = make_desc(T, devices[0]);
-        check(ggp_init_stats(&whole, init_f, init_r), "ggp_init_stats");
-        for (int k = 0; k < D; ++k)
-            if (tables_[k].n_cells() > 0) forests_.emplace_back(new DeviceForest(tables_[k], devices[k], init_f, init_r));
-            else forests_.emplace_back(nullptr);
+    GroupForest(const LineageTable& T, const std::vector<int>& devices) : table_(T) {
+        const ggp_forest_desc d = make_desc(T, devices[0]);
+        std::vector<int32_t> dev(devices.begin(), devices.end());
+        check(ggp_group_create(&d, dev.data(), (int32_t)dev.size(), &g_), "ggp_group_create");
+        if (g_fast_likelihood) check(ggp_group_set_mode(g_, GGP_MODE_FAST), "ggp_group_set_mode");
+        int64_t n_roots = 0;
+        for (int64_t c = 0; c < T.n_cells(); ++c) n_roots += T.parent[c] < 0;
+        carry_.assign((size_t)n_roots * 16, 0.0);
     }
+    ~GroupForest() override { ggp_group_destroy(g_); }
+    GroupForest(const GroupForest&) = delete;
     const LineageTable& table() const override { return table_; }
-    ggp_forest* joints_handle() override { return nullptr; }
 
     std::vector<double> loglik(Session& S, const std::vector<std::vector<double>>& P) override {
         std::vector<double> flat;
         for (const auto& p : P) flat.insert(flat.end(), p.begin(), p.end());
-        const int D = (int)forests_.size(), n_vec = (int)P.size();
-        std::vector<LoglikResult> R(D);
-        std::vector<std::thread> th;
-        for (int k = 0; k < D; ++k)
-            if (forests_[k]) th.emplace_back([&, k] { R[k] = forests_[k]->loglik_raw(flat, n_vec, S.fresh); });
-        for (auto& t : th) t.join();
-        std::vector<double> ll(n_vec, 0.0);
-        for (int k = 0; k < D; ++k) {
-            if (!forests_[k]) continue;
-            if (R[k].rc != GGP_OK && R[k].rc != GGP_ERR_NAN) throw std::runtime_error("ggp_loglik (shard " + std::to_string(k) + "): " + R[k].error);
-            for (int v = 0; v < n_vec; ++v) ll[v] = ll[v] + R[k].ll[v];
-        }
-        // first NaN: the first vector that has one; among the shards the tree that comes first in the file
-        for (int v = 0; v < n_vec; ++v) {
-            int64_t best = -1, best_t = -1;
-            for (int k = 0; k < D; ++k)
-                if (forests_[k] && R[k].nan[v].cell >= 0) {
-                    const int64_t g = cells_[k][R[k].nan[v].cell];
-                    if (best < 0 || g < best) { best = g; best_t = R[k].nan[v].t_index; }
-                }
-            if (best >= 0) report_nan(S, table_, best, best_t, P[v]);
-        }
+        const int n_vec = (int)P.size();
+        std::vector<double> ll(n_vec);
+        std::vector<ggp_nan_info> nan(n_vec);
+        const int rc = ggp_group_loglik(g_, flat.data(), n_vec, S.fresh ? nullptr : carry_.data(), ll.data(), nullptr, nan.data());
+        if (rc == GGP_ERR_NAN)
+            for (int v = 0; v < n_vec; ++v)
+                if (nan[v].cell >= 0) report_nan(S, table_, nan[v].cell, nan[v].t_index, P[v]);
+        check(rc, "ggp_group_loglik");
         return ll;
     }
     void predict(const std::vector<double>& P, int n_seg, std::vector<double>& comb) override {
-        comb.assign((size_t)table_.n_ctp() * 20, 0.0);
-        const int D = (int)forests_.size();
-        std::vector<std::vector<double>> part(D);
-        std::vector<std::string> err(D);
-        std::vector<std::thread> th;
-        for (int k = 0; k < D; ++k)
-            if (forests_[k]) th.emplace_back([&, k] {
-                try { forests_[k]->predict(P, n_seg, part[k]); } catch (std::exception& e) { err[k] = e.what(); }
-            });
-        for (auto& t : th) t.join();
-        for (int k = 0; k < D; ++k) {
-            if (!err[k].empty()) throw std::runtime_error(err[k]);
-            for (size_t i = 0; i < ctp_[k].size(); ++i) std::memcpy(&comb[20 * (size_t)ctp_[k][i]], &part[k][20 * i], 20 * sizeof(double));
-        }
+        comb.resize((size_t)table_.n_ctp() * 20);
+        check(ggp_group_predict(g_, P.data(), n_seg, nullptr, nullptr, comb.data()), "ggp_group_predict");
+    }
+    int joints(const std::vector<double>& P, int n_seg, double tol, int64_t r0, int64_t r1, int64_t cap, int64_t* n, int64_t* row,
+               int64_t* col, double* rec) override {
+        return ggp_group_joints(g_, P.data(), n_seg, tol, r0, r1, cap, n, row, col, rec);
+    }
+    int correlation_sums(const std::vector<double>& P, int n_seg, double tol, double step, int n_bins, double atol, bool normalize_time,
+                         double* hi, double* lo, int64_t* n_joints) override {
+        return ggp_group_correlation_sums(g_, P.data(), n_seg, tol, step, n_bins, atol, normalize_time ? 1 : 0, hi, lo, n_joints);
     }
 
 private:
     const LineageTable& table_;
-    std::vector<LineageTable> tables_;
-    std::vector<std::vector<int64_t>> cells_, ctp_;
-    std::vector<std::unique_ptr<DeviceForest>> forests_;
+    ggp_group* g_ = nullptr;
+    std::vector<double> carry_;   // the roots' persistent covariance in the table's root order
 };
 
 std::unique_ptr<Forest> make_forest(Session& S, const LineageTable& T) {
-    if (S.devices.size() > 1) return std::unique_ptr<Forest>(new ShardedForest(T, S.devices));
+    if (S.devices.size() > 1) return std::unique_ptr<Forest>(new GroupForest(T, S.devices));
     return std::unique_ptr<Forest>(new DeviceForest(T, S.devices[0]));
 }
 
@@ -500,35 +444,26 @@ const int64_t kJointRowBlock = 32768;   // start points per ggp_joints call
 
 // Records of the start points [r0, r1) in (row, col) order.  One library call when the buffers of the previous block
 // were large enough (they grow with the densest block seen), otherwise a second one with the exact size.
-void fetch_joints(ggp_forest* handle, const std::vector<double>& P, int n_seg, double tol, int64_t r0, int64_t r1,
+void fetch_joints(Forest& Fx, const std::vector<double>& P, int n_seg, double tol, int64_t r0, int64_t r1,
                   std::vector<int64_t>& row, std::vector<int64_t>& col, std::vector<double>& rec, int64_t& n) {
     int64_t cap = (int64_t)std::min(row.size(), std::min(col.size(), rec.size() / 44));
     if (cap < 64 * (r1 - r0)) {
         cap = 64 * (r1 - r0);
         row.resize(cap); col.resize(cap); rec.resize((size_t)cap * 44);
     }
-    check(ggp_joints(handle, P.data(), n_seg, tol, r0, r1, cap, &n, row.data(), col.data(), rec.data()), "ggp_joints");
+    check(Fx.joints(P, n_seg, tol, r0, r1, cap, &n, row.data(), col.data(), rec.data()), "ggp_joints");
     if (n > cap) {
         cap = n + n / 8;
         row.resize(cap); col.resize(cap); rec.resize((size_t)cap * 44);
-        check(ggp_joints(handle, P.data(), n_seg, tol, r0, r1, cap, &n, row.data(), col.data(), rec.data()), "ggp_joints");
+        check(Fx.joints(P, n_seg, tol, r0, r1, cap, &n, row.data(), col.data(), rec.data()), "ggp_joints");
     }
 }
 
 void run_joint_distribution(Session& S, Forest& Fx, std::vector<ParameterSet>& list) {
     S.log << "-> joint posteriors\n";
     const LineageTable& T = Fx.table();
-    // the joints follow both daughters of every cell and are written in the file's row order: they run on one handle
-    // that holds the whole table (with several devices: a second pass of -p on the first device)
-    std::unique_ptr<DeviceForest> whole;
-    ggp_forest* handle = Fx.joints_handle();
-    if (!handle) {
-        S.log << "(joints run on device " << S.devices[0] << " only)\n";
-        whole.reset(new DeviceForest(T, S.devices[0]));
-        std::vector<double> tmp;
-        whole->predict(flatten_params(list), (int)list.size(), tmp);
-        handle = whole->handle();
-    }
+    // run_prediction_segments has left the predictions on the data set's handle(s); with several devices every shard walks its
+    // own trees and the records come back in the table's row order (ggp_group_joints)
     const std::vector<double> P = flatten_params(list);
     const double tol = std::stod(S.args["rel_tolerance_joints"]);
     const bool sparse = S.args.count("sparse_joints") > 0;
@@ -552,7 +487,7 @@ void run_joint_distribution(Session& S, Forest& Fx, std::vector<ParameterSet>& l
     for (int64_t r0 = 0; r0 < M; r0 += block) {
         const int64_t r1 = std::min(M, r0 + block);
         int64_t n = 0;
-        fetch_joints(handle, P, (int)list.size(), tol, r0, r1, row, col, rec, n);
+        fetch_joints(Fx, P, (int)list.size(), tol, r0, r1, row, col, rec, n);
         int64_t at = 0;
         for (int64_t r = r0; r < r1; ++r) {
             const int64_t c = cell_of[r];
@@ -588,26 +523,19 @@ void run_correlation(Session& S, Forest& Fx, std::vector<ParameterSet>& list) {
     const LineageTable& T = Fx.table();
     const std::vector<double> P = flatten_params(list);
     const double tol = std::stod(S.args["rel_tolerance_joints"]);
-    std::unique_ptr<DeviceForest> whole;
-    ggp_forest* handle = Fx.joints_handle();
     std::vector<double> comb;
-    if (!handle) {
-        whole.reset(new DeviceForest(T, S.devices[0]));
-        handle = whole->handle();
-    }
     CorrelationSet CS = make_correlation_set(S);
     // the lag-binned sums are accumulated on the device (ggp_correlation_sums: neither a joints file nor a record leaves the GPU);
-    // the host reduction of the sparse records remains for what the device path refuses (more than 256 lags, parents stored
-    // after their daughters) and for GGP_B200_CORR_HOST=1 (A/B comparison)
+    // the host reduction of the sparse records remains for what the device path refuses (parents stored after their daughters)
+    // and for GGP_B200_CORR_HOST=1 (A/B comparison)
     bool on_device = false;
     if (!getenv("GGP_B200_CORR_HOST")) {
-        // run_prediction_segments has left the predictions on the data set's own handle; a handle made here needs them first
-        if (whole) check(ggp_predict(handle, P.data(), (int32_t)list.size(), nullptr, nullptr, nullptr), "ggp_predict");
+        // run_prediction_segments has left the predictions on the data set's own handle(s)
         std::vector<double> hi(CS.bins.size() * 50), lo(CS.bins.size() * 50);
         int64_t n_joints = 0;
         const double step = CS.bins.size() > 1 ? CS.bins[1].dt - CS.bins[0].dt : 1.0;
-        const int rc = ggp_correlation_sums(handle, P.data(), (int32_t)list.size(), tol, step, (int32_t)CS.bins.size(), CS.tol,
-                                            S.args.count("normalize_time") > 0, hi.data(), lo.data(), &n_joints);
+        const int rc = Fx.correlation_sums(P, (int)list.size(), tol, step, (int)CS.bins.size(), CS.tol,
+                                           S.args.count("normalize_time") > 0, hi.data(), lo.data(), &n_joints);
         if (rc == GGP_OK) {
             CS.set_sums(hi.data(), lo.data());
             S.log << "   " << n_joints << " joints reduced into " << CS.bins.size() << " lag bins on the device\n";
@@ -619,8 +547,7 @@ void run_correlation(Session& S, Forest& Fx, std::vector<ParameterSet>& list) {
         }
     }
     if (!on_device) {
-    comb.resize((size_t)T.n_ctp() * 20);
-    check(ggp_predict(handle, P.data(), (int32_t)list.size(), nullptr, nullptr, comb.data()), "ggp_predict");
+    Fx.predict(P, (int)list.size(), comb);
     std::vector<double> m14((size_t)T.n_ctp() * 14);
     for (int64_t k = 0; k < T.n_ctp(); ++k) {
         const double* r = comb.data() + 20 * k;
@@ -634,7 +561,7 @@ void run_correlation(Session& S, Forest& Fx, std::vector<ParameterSet>& list) {
     src.joints_of_rows = [&](int64_t r0, int64_t r1, std::vector<int64_t>& row, std::vector<int64_t>& col, std::vector<double>& rec) {
         int64_t n = 0;
         row.resize(row.capacity()); col.resize(col.capacity());   // reuse what the previous block grew to
-        fetch_joints(handle, P, (int)list.size(), tol, r0, r1, row, col, rec, n);
+        fetch_joints(Fx, P, (int)list.size(), tol, r0, r1, row, col, rec, n);
         row.resize(n); col.resize(n);
     };
     correlation_from_joints(CS, T.cell_id, T.parent_id, T.offset, T.time, src, S.args.count("normalize_time") > 0, kJointRowBlock);

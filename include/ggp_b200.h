@@ -168,7 +168,7 @@ int ggp_joints(ggp_forest* f, const double* params, int32_t n_seg, double rel_to
  *                           per-block partials added in long double; each entry is the leading double of its sum,
  *   out_sums_lo             NULL or [n_bins][50]: the remainder (sum - leading double),
  *   out_joints              NULL or the number of joints the walk emitted.
- * Requires a prior ggp_predict with the same params, at most 256 bins, and parents stored before their daughters (else
+ * Requires a prior ggp_predict with the same params, fewer than 65 535 bins, and parents stored before their daughters (else
  * GGP_ERR_BAD_ARG: reduce the sparse records of ggp_joints on the host, host/ggp_correlation.hpp). */
 int ggp_correlation_sums(ggp_forest* f, const double* params, int32_t n_seg, double rel_tol, double dt_step, int32_t n_bins,
                          double atol, int32_t normalize_time, double* out_sums, double* out_sums_lo, int64_t* out_joints);
@@ -180,8 +180,8 @@ int ggp_correlation_sums(ggp_forest* f, const double* params, int32_t n_seg, dou
  * per-cell sums, root_carry and prediction rows come back in the caller's order.  A data set stored tree by tree is split into
  * contiguous runs of trees, so each device copies its prediction rows straight into their place in the caller's arrays;
  * otherwise trees are bin-packed by size and the rows are scattered back by index.  Same argument meaning and error
- * behaviour as the single-forest calls; joints run per member (ggp_group_member + ggp_group_member_ctp give the handles and
- * the index maps).  `devices` may name a device more than once. */
+ * behaviour as the single-forest calls (ggp_group_member + ggp_group_member_ctp give the members' handles and
+ * index maps).  `devices` may name a device more than once. */
 typedef struct ggp_group ggp_group;
 int ggp_group_create(const ggp_forest_desc* desc, const int32_t* devices, int32_t n_devices, ggp_group** out);   /* desc->device is ignored */
 void ggp_group_destroy(ggp_group* g);
@@ -196,6 +196,14 @@ int ggp_group_loglik(ggp_group* g, const double* params, int32_t n_vec, double* 
 int ggp_group_predict(ggp_group* g, const double* params, int32_t n_seg, double* out_forward, double* out_backward, double* out_combined);
 int ggp_group_predict14(ggp_group* g, const double* params, int32_t n_seg, double* out_forward14, double* out_backward14,
                         double* out_combined14);
+/* ggp_joints over the shards (collect_joint_distributions, correlation_tree.h:629-648): rows, columns and the row range are the
+ * CALLER's time-point indices, records sorted by (row, col); requires a prior ggp_group_predict[14] with the same params.  Every
+ * shard counts first: if the total exceeds `cap` only *out_count is written. */
+int ggp_group_joints(ggp_group* g, const double* params, int32_t n_seg, double rel_tol, int64_t row_begin, int64_t row_end, int64_t cap,
+                     int64_t* out_count, int64_t* row_ctp, int64_t* col_ctp, double* rec44);
+/* ggp_correlation_sums over the shards: the sums run over pairs of points of one lineage tree, so they add over shards */
+int ggp_group_correlation_sums(ggp_group* g, const double* params, int32_t n_seg, double rel_tol, double dt_step, int32_t n_bins,
+                               double atol, int32_t normalize_time, double* out_sums, double* out_sums_lo, int64_t* out_joints);
 
 /* waits for the evaluation enqueued by ggp_loglik_device and returns its device time in milliseconds */
 int ggp_sync_kernel_ms(ggp_forest* f, double* ms_out);

@@ -222,3 +222,17 @@ def test_devices_option_shards_trees(tmp_path):
         outs.append((np.array([[float(x) for x in r[1:]] for r in sc]), pr, jn))
     assert outs[0][1] == outs[1][1] and outs[0][2] == outs[1][2]
     assert max_rel(outs[1][0][:, 11], outs[0][0][:, 11]) < 1e-13 and np.array_equal(outs[1][0][:, :11], outs[0][0][:, :11])
+    # the correlation functions: every shard reduces its own trees' joints on its device, the sums add (ggp_group_correlation_sums)
+    dt = repr(float(data.time[1] - data.time[0]))
+    tabs = []
+    for extra, name in (([], "corr_one"), (["--devices", "0,0,0"], "corr_three")):
+        out = str(tmp_path / name)
+        run(["-i", csv, "-b", pf, "-c", cfg, "-p", "--correlation", dt, "--n_data", "15", "-o", out] + extra)
+        log = open([os.path.join(out, f) for f in os.listdir(out) if f.endswith("_success.log")][0]).read()
+        assert "lag bins on the device" in log
+        lines = open(os.path.join(out, "forest_f_b3_correlations.csv")).read().strip().split("\n")
+        tabs.append(np.array([[float(x) if x else np.nan for x in l.split(",")] for l in lines[1:]]))
+    a, b = tabs
+    assert a.shape == b.shape and np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(a[:, -1], b[:, -1])
+    ok = ~np.isnan(a)
+    assert np.allclose(a[ok], b[ok], rtol=1e-9, atol=1e-12)

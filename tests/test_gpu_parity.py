@@ -434,6 +434,21 @@ def test_group_handle_shards_one_data_set_over_devices(ragged):
     for k in ("forward", "backward", "prediction"):
         assert same_bits(got[k][:, :4], full[k][0]) and same_bits(got[k][:, 4:], full[k][1].reshape(-1, 16))
         assert same_bits(got14[k][:, :4], full[k][0]) and same_bits(got14[k][:, 4:], full[k][1].reshape(-1, 16)[:, iu])
+    # joints and the lag-binned correlation sums over the shards: every shard walks its own trees; rows / columns are the
+    # caller's time-point indices in (row, col) order, the sums add over shards
+    r, c, m, v = ggp.collect_joint_distributions(f, P, 1e-10)
+    rg, cg, mg, vg = g.joints(P, 1e-10)
+    assert len(r) > 100 and np.array_equal(r, rg) and np.array_equal(c, cg) and same_bits(m, mg) and same_bits(v, vg)
+    lo, hi = d.n_ctp // 3, 2 * d.n_ctp // 3
+    sel = (r >= lo) & (r < hi)
+    rb, cb, mb, vb = g.joints(P, 1e-10, row_begin=lo, row_end=hi)
+    assert np.array_equal(rb, r[sel]) and np.array_equal(cb, c[sel]) and same_bits(vb, v[sel])
+    if not ragged:   # (the ragged toy stores a parent after its daughter: the device reduction refuses it, the host path remains)
+        dt = float(d.time[1] - d.time[0])
+        s_f, n_f = ggp.api.correlation_sums(f, P, dt, 60)
+        s_g, n_g = g.correlation_sums(P, dt, 60)
+        assert n_f == n_g == len(r) and np.array_equal(s_f[:, 0], s_g[:, 0])
+        assert np.allclose(np.asarray(s_f, dtype=np.float64), np.asarray(s_g, dtype=np.float64), rtol=1e-14, atol=1e-300)
     g.set_mode("fast")
     assert max_rel(g.total_likelihood(vecs), ll_f) <= 1e-10
     g.close()

@@ -568,6 +568,21 @@ def measure_one_process(ggp, torch, n_dev, args, whole, P):
                                    "ctp_per_s": data.n_ctp / float(np.min(ts[1:])), "d2h_bytes": int(3 * 14 * 8 * data.n_ctp),
                                    "finite": bool(np.isfinite(pins["prediction"][::997]).all())}
     g.close()
+    # configs[4] (-j on 100 k cells, two segments) with the correlation reduction, every device on its own trees
+    P2 = np.stack([ggp.PARAMS_SCALED_BINOMIAL, ggp.PARAMS_SCALED_BINOMIAL * np.array([1, 1, 1, 2, 1, 1, 1, 1, 1, 1, 1.])])
+    data = ggp.simulate_forest(1587, 6, params=ggp.PARAMS_SCALED_BINOMIAL, noise_model="scaled", division_model="binomial",
+                               seed=20261018, n_segments=2)
+    g = ggp.ForestGroup(data, list(range(n_dev)))
+    g.predictions(P2, packed=True)
+    ts, nj = [], 0
+    for _ in range(3):
+        t0 = time.perf_counter()
+        sums, nj = g.correlation_sums(P2, 15.0, 200)
+        ts.append(time.perf_counter() - t0)
+    out["cfg5_correlation_sharded"] = {"n_cells": int(data.n_cells), "joints": int(nj), "e2e_ms": float(np.min(ts[1:])) * 1e3,
+                                       "joints_per_s": nj / float(np.min(ts[1:])),
+                                       "what": "ggp_group_correlation_sums: walk + lag-binned reduction on every device, sums added on the host"}
+    g.close()
     return out
 
 

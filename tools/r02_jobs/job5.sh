@@ -1,7 +1,7 @@
 #!/bin/bash
 O=gpurun_out
 python -m pytest tests/test_correlation.py tests/test_gpu_configs.py tests/test_gpu_parity.py -m gpu -x -q -k "joint or corr or lag" 2>&1 | tail -3
-python tools/scratch/corr_probe.py 3 2>&1 | tee $O/corr_probe_r02c.txt
+python tools/r02_jobs/corr_probe.py 3 2>&1 | tee $O/corr_probe_r02c.txt
 python - <<'P' 2>&1 | tee $O/walk_probe_r02c.txt
 import sys, time, numpy as np
 sys.path.insert(0, '.')

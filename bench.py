@@ -45,12 +45,12 @@ F_ALG_PREDICT = 8900.0   # -p: 2 F_alg + 1 500 (combine)
 F_ALG_JOINT = 5500.0     # -j: per emitted joint
 B_ALG = 28.0          # algorithmic bytes per cell-timepoint: time, x, g (f64) + segment (i32)
 # dram__bytes_read.sum + dram__bytes_write.sum per cell-timepoint from the ncu --set full captures of the largest
-# generation's launch (6 399 691 ctp): strict profiles/r01_s5_loglik_coop_gen5.txt, fast profiles/r02_fast5_poly_gen5.txt
-DRAM_BYTES_PER_CTP_NCU = {"strict": (204.285440e6 + 4.971776e6) / 6399691.0, "fast": (144.559872e6 + 4.336640e6) / 6399691.0}
-# what the fast kernel EXECUTES per cell-timepoint with the 5-node rule (same capture: 66.39 M DFMA, 21.49 M DMUL, 9.77 M DADD
+# generation's launch (6 399 691 ctp): strict profiles/r01_s5_loglik_coop_gen5.txt, fast profiles/r02_fast5_final_gen5.txt
+DRAM_BYTES_PER_CTP_NCU = {"strict": (204.285440e6 + 4.971776e6) / 6399691.0, "fast": (130.749952e6 + 4.492032e6) / 6399691.0}
+# what the fast kernel EXECUTES per cell-timepoint with the 5-node rule (same capture: 59.53 M DFMA, 21.71 M DMUL, 9.77 M DADD
 # warp instructions for 6 399 691 ctp), an FMA counted as two flops
-FAST_EXEC = {"nodes": 5, "dfma": 66392317 * 32 / 6399691.0, "dmul": 21490749 * 32 / 6399691.0, "dadd": 9770336 * 32 / 6399691.0,
-             "instr": 134042100 * 32 / 6399691.0, "fp64_pipe_busy": 0.698}
+FAST_EXEC = {"nodes": 5, "dfma": 59528912 * 32 / 6399691.0, "dmul": 21709416 * 32 / 6399691.0, "dadd": 9770336 * 32 / 6399691.0,
+             "instr": 129461032 * 32 / 6399691.0, "fp64_pipe_busy": 0.704}
 METRIC = "cell-timepoints/s, FP64 log-likelihood evaluation (loglik evals/s in config)"
 GATE = 1e-10          # north star: log-likelihood within relative 1e-10 of the reference
 
@@ -450,7 +450,7 @@ def run_ours(args):
                     "note": ("F_alg counts the reference's formulas (38 integrals via Dawson, 26 exp, 3 pow per step); the fast kernel "
                              "evaluates the same moments by quadrature with 3 N short exponentials and no Dawson / pow, so `frac` is "
                              "ALGORITHMIC work per second over the DFMA peak and exceeds 1; `executed` is what the kernel really does "
-                             "(ncu, 5 nodes: 670 instructions / 488 FP64 per ctp, FP64 pipe 69.8 % busy, profiles/r02_fast5_poly_gen5.txt)")
+                             "(ncu, 5 nodes: 647 instructions / 455 FP64 per ctp, FP64 pipe 70.4 % busy, profiles/r02_fast5_final_gen5.txt)")
                     if mode == "fast" else
                             ("strict arithmetic cannot fuse (FMA off) and evaluates 66 exp + 14 Dawson + 3 pow per step bit for bit: "
                              "3 220 executed FP64 instructions per ctp, FP64 pipe busy 44.5 % (profiles/r01_s5_loglik_coop_gen5.txt)"),

@@ -456,6 +456,22 @@ def test_group_handle_shards_one_data_set_over_devices(ragged):
 
 
 @pytest.mark.gpu
+def test_group_handles_come_and_go():
+    """a group owns one worker thread per shard: created, used and destroyed repeatedly (also unused, and with more shards than
+    trees: empty shards have no member and no work), results unchanged"""
+    d = ggp.simulate_forest(3, 3, seed=5)
+    f = ggp.Forest(d)
+    want = ggp.total_likelihood(ggp.PARAMS_CONST_GAUSS, f, per_cell=True)[1]
+    f.close()
+    for rep in range(12):
+        g = ggp.ForestGroup(d, [0] * (1 + rep % 5))
+        if rep % 3:
+            for _ in range(3):
+                assert same_bits(g.total_likelihood(ggp.PARAMS_CONST_GAUSS, per_cell=True)[1], want)
+        g.close()
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("seed", [101, 102, 103, 104])
 def test_random_forests_all_passes_bitwise(seed):
     """random shapes (tree counts that do not fill a 32-cell group, very short and long cells, 1-3 segments, both models):

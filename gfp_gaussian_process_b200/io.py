@@ -155,3 +155,54 @@ def read_data(path, cfg: CSVConfig = None, noise_model="scaled", division_model=
                        fp=np.array(g), segment=np.array(seg, dtype=np.int32), noise_model=noise_model,
                        division_model=division_model, fp_auto=cfg.fp_auto)
     return data, cell_ids
+
+
+# ---- binary forest file (layout in host/ggp_data.hpp::read_binary_forest) -------------------------------
+_MAGIC = b"GGPFORE1"
+
+
+def write_forest_binary(path, data, cell_ids=None, parent_ids=None):
+    """LineageData -> the binary forest file `gfp_gaussian -i` reads instead of a csv.  cell_ids / parent_ids: the id strings the
+    output files print (default: the cell's number from 1, the parent's number or 0 for a root)."""
+    import struct
+    n_cells, n_ctp = int(data.n_cells), int(data.n_ctp)
+    if cell_ids is None:
+        cell_ids = [str(c + 1) for c in range(n_cells)]
+    if parent_ids is None:
+        parent_ids = [str(int(p) + 1) if p >= 0 else "0" for p in data.parent]
+    with open(path, "wb") as f:
+        f.write(_MAGIC)
+        f.write(struct.pack("<qq", n_cells, n_ctp))
+        f.write(np.ascontiguousarray(data.cell_offset, dtype="<i8").tobytes())
+        for a in (data.time, data.log_length, data.fp):
+            f.write(np.ascontiguousarray(a, dtype="<f8").tobytes())
+        f.write(np.ascontiguousarray(data.segment, dtype="<i4").tobytes())
+        for c, p in zip(cell_ids, parent_ids):
+            for s in (c, p):
+                b = str(s).encode()
+                f.write(struct.pack("<I", len(b)))
+                f.write(b)
+
+
+def read_forest_binary(path, noise_model="scaled", division_model="binomial"):
+    """binary forest file -> (LineageData, cell_ids, parent_ids); parents are resolved like the csv reader does (a cell's parent is
+    the cell whose id equals its parent id)"""
+    import struct
+    from .forest import LineageData
+    with open(path, "rb") as f:
+        if f.read(8) != _MAGIC:
+            raise ValueError("not a binary forest file: " + str(path))
+        n_cells, n_ctp = struct.unpack("<qq", f.read(16))
+        off = np.frombuffer(f.read(8 * (n_cells + 1)), dtype="<i8").astype(np.int64)
+        time, x, g = (np.frombuffer(f.read(8 * n_ctp), dtype="<f8").astype(np.float64) for _ in range(3))
+        seg = np.frombuffer(f.read(4 * n_ctp), dtype="<i4").astype(np.int32)
+        ids = []
+        for _ in range(2 * n_cells):
+            (n,) = struct.unpack("<I", f.read(4))
+            ids.append(f.read(n).decode())
+    cell_ids, parent_ids = ids[0::2], ids[1::2]
+    index = {c: i for i, c in enumerate(cell_ids)}
+    parent = np.array([index.get(p, -1) for p in parent_ids], dtype=np.int64)
+    data = LineageData(cell_offset=off, parent=parent, time=time, log_length=x, fp=g, segment=seg, noise_model=noise_model,
+                       division_model=division_model)
+    return data, cell_ids, parent_ids

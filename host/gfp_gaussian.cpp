@@ -710,7 +710,9 @@ int main(int argc, char** argv) {
         CsvConfig config(S.args["csv_config"], &S.log);
         S.log << config << "\n";
         S.log << "-> Reading\n";
-        LineageTable cells = read_data(S.args["infile"], config, S.args["noise_model"], S.args["cell_division_model"], S.log);
+        LineageTable cells = is_binary_forest(S.args["infile"])
+                                 ? read_binary_forest(S.args["infile"], config, S.args["noise_model"], S.args["cell_division_model"], S.log)
+                                 : read_data(S.args["infile"], config, S.args["noise_model"], S.args["cell_division_model"], S.log);
         const std::vector<int> segs = segment_indices(cells, S.log);
         if (segs.size() != param_files.size()) {
             S.log << "(main) ERROR: There are " << segs.size() << " segments, but " << param_files.size() << " parameter files!\n";

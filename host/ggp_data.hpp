@@ -162,6 +162,64 @@ inline LineageTable read_data(const std::string& filename, const CsvConfig& cfg,
     return T;
 }
 
+// ---- binary forest file: the table as it is handed to the C ABI, for data sets that are too large to be
+// worth parsing as text (a 12.6 M-row csv is 600 MB of digits) and for synthetic forests.  Little endian:
+//   char magic[8] = "GGPFORE1"; int64 n_cells, n_ctp; int64 cell_offset[n_cells + 1]; double time[n_ctp], log_length[n_ctp],
+//   fp[n_ctp]; int32 segment[n_ctp]; then per cell: uint32 length + bytes of its cell id, uint32 length + bytes of its parent id.
+// Times are final (no rescale_time), lengths are logarithms, there is no filter column; fp_auto still comes from the csv_config.
+// Written by gfp_gaussian_process_b200/io.py::write_forest_binary.
+inline bool is_binary_forest(const std::string& filename) {
+    std::ifstream f(filename, std::ios::binary);
+    char magic[8] = {};
+    f.read(magic, 8);
+    return f.gcount() == 8 && std::string(magic, 8) == "GGPFORE1";
+}
+
+inline LineageTable read_binary_forest(const std::string& filename, const CsvConfig& cfg, const std::string& noise_model,
+                                       const std::string& division_model, std::ostream& log) {
+    std::ifstream f(filename, std::ios::binary);
+    LineageTable T;
+    T.noise_model = noise_model; T.division_model = division_model; T.fp_auto = cfg.fp_auto;
+    auto fail = [&](const char* what) {
+        log << "(read_binary_forest) ERROR: " << what << " in " << filename << "\n";
+        throw std::invalid_argument("Invalid argument");
+    };
+    char magic[8];
+    int64_t n_cells = 0, n_ctp = 0;
+    f.read(magic, 8);
+    f.read(reinterpret_cast<char*>(&n_cells), 8);
+    f.read(reinterpret_cast<char*>(&n_ctp), 8);
+    if (!f || std::string(magic, 8) != "GGPFORE1" || n_cells <= 0 || n_ctp < n_cells) fail("bad header");
+    auto read_array = [&](auto& v, int64_t n) {
+        v.resize((size_t)n);
+        f.read(reinterpret_cast<char*>(v.data()), (std::streamsize)(n * (int64_t)sizeof(v[0])));
+        if (!f) fail("file ends inside an array");
+    };
+    read_array(T.offset, n_cells + 1);
+    read_array(T.time, n_ctp);
+    read_array(T.log_length, n_ctp);
+    read_array(T.fp, n_ctp);
+    read_array(T.segment, n_ctp);
+    if (T.offset.front() != 0 || T.offset.back() != n_ctp) fail("cell offsets do not cover the time points");
+    for (int64_t c = 0; c < n_cells; ++c) if (T.offset[c + 1] <= T.offset[c]) fail("a cell without a time point");
+    auto read_string = [&]() {
+        uint32_t len = 0;
+        f.read(reinterpret_cast<char*>(&len), 4);
+        if (!f || len > (1u << 20)) fail("bad id string");
+        std::string s(len, '\0');
+        f.read(&s[0], len);
+        if (!f) fail("file ends inside an id");
+        return s;
+    };
+    T.cell_id.reserve((size_t)n_cells); T.parent_id.reserve((size_t)n_cells);
+    for (int64_t c = 0; c < n_cells; ++c) {
+        T.cell_id.push_back(read_string());
+        T.parent_id.push_back(read_string());
+    }
+    log << T.n_cells() << " cells and " << n_ctp << " data points found in binary file " << filename << std::endl;
+    return T;
+}
+
 // segment indices in order of first occurrence; must be 0..n-1 (moma_input.h:538-570)
 inline std::vector<int> segment_indices(const LineageTable& T, std::ostream& log) {
     std::vector<int> segs;

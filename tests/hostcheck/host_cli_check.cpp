@@ -21,7 +21,8 @@ long hcli_load(const char* infile, const char* config, int segment) {
     std::ostringstream log;
     try {
         CsvConfig cfg(config, &log);
-        LineageTable T = read_data(infile, cfg, "scaled", "binomial", log);
+        LineageTable T = is_binary_forest(infile) ? read_binary_forest(infile, cfg, "scaled", "binomial", log)
+                                                  : read_data(infile, cfg, "scaled", "binomial", log);
         segment_indices(T, log);
         if (segment >= 0) T = get_segment(T, segment);
         build_genealogy(T, log);

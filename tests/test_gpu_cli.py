@@ -236,3 +236,21 @@ def test_devices_option_shards_trees(tmp_path):
     assert a.shape == b.shape and np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(a[:, -1], b[:, -1])
     ok = ~np.isnan(a)
     assert np.allclose(a[ok], b[ok], rtol=1e-9, atol=1e-12)
+
+
+def test_binary_forest_input_gives_the_same_files(tmp_path):
+    """-i forest.ggpf (binary forest file) instead of the csv of the same data: identical scan, prediction and joints files"""
+    from gfp_gaussian_process_b200 import io
+    P = ggp.PARAMS_SCALED_BINOMIAL
+    data = ggp.simulate_forest(7, 3, noise_model="scaled", division_model="binomial", seed=29, pts_range=(3, 8))
+    csv, cfg = write_inputs(tmp_path, data)
+    binf = str(tmp_path / "forest.ggpf")
+    io.write_forest_binary(binf, data, ["1.%d" % (c + 1) for c in range(data.n_cells)],
+                           ["1.%d" % (int(p) + 1 if p >= 0 else 0) for p in data.parent])
+    pf = write_params(tmp_path / "p.txt", P, bound=(3,))
+    outs = []
+    for infile, name in ((csv, "csv"), (binf, "bin")):
+        out = str(tmp_path / name)
+        run(["-i", infile, "-b", pf, "-c", cfg, "-s", "-p", "-j", "--sparse_joints", "-o", out])
+        outs.append([open(os.path.join(out, "forest_" + f)).read() for f in ("scan_mean_q.csv", "f_b3_prediction.csv", "f_b3_joints.csv")])
+    assert outs[0] == outs[1]

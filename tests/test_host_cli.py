@@ -199,3 +199,34 @@ def test_python_reader_composes_ids_like_the_cpp_reader(hc, tmp_path):
     with pytest.raises(ValueError):
         ggio.read_data(csv, ggio.read_csv_config(cfg))
     assert hc.hcli_load(csv.encode(), cfg.encode(), -1) == -1
+
+
+def test_binary_forest_file_round_trip(hc, tmp_path):
+    """the binary forest file: written by the Python layer, read by the command line's loader and by the
+    Python reader with the same arrays (bits), ids and genealogy as the csv of the same data; damaged files are refused"""
+    from conftest import ragged_forest
+    from gfp_gaussian_process_b200 import io
+    d = ragged_forest()
+    ids = ["1." + str(100 + c) for c in range(d.n_cells)]
+    pids = [ids[p] if p >= 0 else "1.7" for p in d.parent]
+    path = str(tmp_path / "forest.ggpf")
+    io.write_forest_binary(path, d, ids, pids)
+    cfg = str(tmp_path / "cfg.txt")
+    open(cfg, "w").write("fp_auto = 3\n")
+    got = load(hc, path, cfg)
+    assert "binary file" in hc.hcli_text().decode() and got["ids"] == ids
+    assert np.array_equal(got["off"], d.cell_offset) and np.array_equal(got["parent"], d.parent)
+    assert np.array_equal(got["d1"], d.daughter1) and np.array_equal(got["d2"], d.daughter2) and np.array_equal(got["seg"], d.segment)
+    for k, a in (("time", d.time), ("x", d.log_length), ("g", d.fp)):
+        assert np.array_equal(got[k].view(np.uint64), np.asarray(a, dtype=np.float64).view(np.uint64))
+    seg1 = load(hc, path, cfg, segment=1)                              # segment slicing works on it like on a csv
+    assert seg1["time"].size == int((d.segment == 1).sum())
+    back, cid, pid = io.read_forest_binary(path)
+    assert cid == ids and pid == pids and np.array_equal(back.parent, d.parent) and np.array_equal(back.cell_offset, d.cell_offset)
+    assert np.array_equal(back.fp.view(np.uint64), np.asarray(d.fp, dtype=np.float64).view(np.uint64))
+    io.write_forest_binary(str(tmp_path / "default_ids.ggpf"), d)      # default ids: numbers from 1, 0 for "no parent"
+    got2 = load(hc, str(tmp_path / "default_ids.ggpf"), cfg)
+    assert got2["ids"][:3] == ["1", "2", "3"] and np.array_equal(got2["parent"], d.parent)
+    raw = open(path, "rb").read()
+    open(str(tmp_path / "cut.ggpf"), "wb").write(raw[:len(raw) // 2])
+    assert hc.hcli_load(str(tmp_path / "cut.ggpf").encode(), cfg.encode(), -1) == -1 and "file ends" in hc.hcli_text().decode()

@@ -69,6 +69,27 @@ if "cfg1" in which:   # the example data set (one tree, 77 cells, 22 065 points)
         stopped = [l for l in log.split("\n") if l.startswith("Stopped") or l.startswith("Found maximum")]
         out(config="cfg1 example data set, gfp_gaussian -m -p " + " ".join(extra), rc=r.returncode, wall_s=dt, log=stopped)
 
+if "cfg2" in which:   # the command line on a configs[1]-size data set: binary forest file in, 1-d scan of mean_q (17 evaluations in one launch)
+    from gfp_gaussian_process_b200 import io
+    from test_gpu_cli import write_params, CLI
+    import pathlib
+    tmp = pathlib.Path(tempfile.mkdtemp())
+    data = ggp.simulate_forest(10000, 6, seed=20261018)
+    t = time.perf_counter()
+    io.write_forest_binary(str(tmp / "forest.ggpf"), data)
+    t_write = time.perf_counter() - t
+    open(tmp / "cfg.txt", "w").write("fp_auto = 0\n")
+    P = ggp.PARAMS_CONST_GAUSS
+    pf = write_params(tmp / "p.txt", P, bound=(3,))
+    for extra, name in ((["--fast"], "fast"), (["--fresh"], "fresh")):
+        t = time.perf_counter()
+        r = subprocess.run(["timeout", "900", CLI, "-i", str(tmp / "forest.ggpf"), "-b", pf, "-c", str(tmp / "cfg.txt"), "-s", "-noise", "const",
+                            "-div", "gauss", "-o", str(tmp / name)] + extra, capture_output=True, text=True)
+        dt = time.perf_counter() - t
+        n_lines = sum(1 for _ in open(tmp / name / "forest_scan_mean_q.csv")) if r.returncode == 0 else -1
+        out(config="cfg2 command line, binary forest file (%d MB) -s mean_q %s" % (os.path.getsize(tmp / "forest.ggpf") >> 20, " ".join(extra)),
+            rc=r.returncode, wall_s=dt, scan_file_lines=n_lines, write_binary_s=t_write, n_ctp=int(data.n_ctp), tail=r.stdout[-300:])
+
 if "cfg3" in which:   # -p on a 1M-cell forest, binomial + scaled (one GPU's worth; 8 GPUs shard the trees)
     data = ggp.simulate_forest(15873, 6, noise_model="scaled", division_model="binomial", seed=20261018)
     f = ggp.Forest(data)

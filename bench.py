@@ -362,7 +362,7 @@ def run_ours(args):
         dev = [torch.empty(a.shape, dtype=a.dtype, device="cuda") for a in pin]
         ts = []
         for _ in range(reps + 1):
-            torch.cuda.synchronize()
+            barrier()   # all ranks copy at the same time: at N > 1 this is the host-side ceiling the end-to-end step shares
             t0 = time.perf_counter()
             for dst, src in zip(dev, pin):
                 dst.copy_(src, non_blocking=True)
@@ -465,8 +465,10 @@ def run_ours(args):
                     "h2d_gbps_per_gpu": 2 * 8 * n_ctp / r["e2e_s"] / 1e9,
                     "pcie": {"copy_alone_ms": pcie_copy_s * 1e3, "copy_alone_gbps_per_gpu": 2 * 8 * n_ctp / pcie_copy_s / 1e9,
                              "frac": pcie_copy_s / r["e2e_s"],
-                             "what": "the step's two pinned arrays copied to the device with nothing else running (max over ranks): "
-                                     "the end-to-end step is bound by this link, frac = copy alone / whole step"},
+                             "what": "the step's two pinned arrays copied to the device with no kernel running, ALL ranks at the same time "
+                                     "(barrier before every copy, max over ranks): the end-to-end step is bound by this path - PCIe at "
+                                     "N = 1, the guest's host side at N = 8 (tools/r02_jobs/h2d_concurrent.py: 55 GB/s per GPU alone, "
+                                     "23.5 - 36 GB/s with eight copying together); frac = copy alone / whole step"},
                     "what": "ggp_forest_upload_series (this step's log_length and fp from pinned host memory with their init_cells "
                             "statistics; the unchanged time grid is not sent again) + ggp_loglik (host params in, host log-likelihood "
                             "and NaN record out), wall clock around the host calls"}

@@ -163,6 +163,22 @@ struct ggp_forest {
         DevBuf<unsigned int> idx, idx2;
         DevBuf<unsigned char> tmp;
     } corr;
+    // scratch of ggp_joints, kept between calls while it stays below GGP_JOINT_SCRATCH_KEEP bytes (the command line fetches row
+    // block after row block: allocating and freeing ~2 GB per call cost more than the walk; a single huge call gives it back)
+    struct {
+        DevBuf<long long> row, col, row2, col2;
+        DevBuf<double> rec, rec2;
+        DevBuf<unsigned long long> count, key, key2;
+        DevBuf<unsigned int> idx, idx2;
+        DevBuf<unsigned char> tmp;
+        size_t bytes() const {
+            return (row.n + col.n + row2.n + col2.n + rec.n + rec2.n + count.n + key.n + key2.n) * 8 + (idx.n + idx2.n) * 4 + tmp.n;
+        }
+        void release() {
+            row.release(); col.release(); row2.release(); col2.release(); rec.release(); rec2.release(); count.release();
+            key.release(); key2.release(); idx.release(); idx2.release(); tmp.release();
+        }
+    } jscratch;
     bool have_prep = false;
     bool have_pred = false;
     int32_t pred_n_seg = 0;

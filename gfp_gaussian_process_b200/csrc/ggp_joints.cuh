@@ -580,7 +580,9 @@ __global__ void __launch_bounds__(GGP_BLOCK) ggp_joint_prep_kernel(const GgpDevF
     }
 }
 
+#ifndef GGP_WALK_BLOCK
 #define GGP_WALK_BLOCK 256
+#endif
 __global__ void __launch_bounds__(GGP_WALK_BLOCK, 1) ggp_joint_walk_kernel(const GgpDevForest F, const GgpJointArgs A) {
     ggp_walk_start_points(F, A, (int64_t)blockIdx.x * GGP_WALK_BLOCK + threadIdx.x);
 }

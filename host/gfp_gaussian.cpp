@@ -56,7 +56,9 @@ public:
     virtual ~Forest() = default;
     virtual const LineageTable& table() const = 0;
     // +log-likelihood of each vector, evaluated as if one after the other (likelihood.h:170-174)
-    virtual std::vector<double> loglik(Session& S, const std::vector<std::vector<double>>& P) = 0;
+    // tolerate_nan: a NaN evaluation is returned as NaN instead of being reported (speculative batches: the search may never
+    // use that point; if it does, the point is evaluated again on its own and reported like the reference does)
+    virtual std::vector<double> loglik(Session& S, const std::vector<std::vector<double>>& P, bool tolerate_nan = false) = 0;
     // combined predictions [n_ctp][20] in the table's ctp order (main.cpp:132-140)
     virtual void predict(const std::vector<double>& P, int n_seg, std::vector<double>& comb) = 0;
     // joints of the start points [r0, r1) in (row, col) order and the lag-binned correlation sums, in the table's ctp indices
@@ -121,13 +123,15 @@ public:
         if (R.rc != GGP_OK && R.rc != GGP_ERR_NAN) R.error = ggp_last_error();
         return R;
     }
-    std::vector<double> loglik(Session& S, const std::vector<std::vector<double>>& P) override {
+    std::vector<double> loglik(Session& S, const std::vector<std::vector<double>>& P, bool tolerate_nan = false) override {
         std::vector<double> flat;
         for (const auto& p : P) flat.insert(flat.end(), p.begin(), p.end());
         LoglikResult R = loglik_raw(flat, (int)P.size(), S.fresh);
-        if (R.rc == GGP_ERR_NAN)
+        if (R.rc == GGP_ERR_NAN) {
+            if (tolerate_nan) return R.ll;
             for (size_t v = 0; v < P.size(); ++v)
                 if (R.nan[v].cell >= 0) report_nan(S, table_, R.nan[v].cell, R.nan[v].t_index, P[v]);
+        }
         if (R.rc != GGP_OK) throw std::runtime_error("ggp_loglik: " + R.error);
         return R.ll;
     }
@@ -160,16 +164,18 @@ public:
     GroupForest(const GroupForest&) = delete;
     const LineageTable& table() const override { return table_; }
 
-    std::vector<double> loglik(Session& S, const std::vector<std::vector<double>>& P) override {
+    std::vector<double> loglik(Session& S, const std::vector<std::vector<double>>& P, bool tolerate_nan = false) override {
         std::vector<double> flat;
         for (const auto& p : P) flat.insert(flat.end(), p.begin(), p.end());
         const int n_vec = (int)P.size();
         std::vector<double> ll(n_vec);
         std::vector<ggp_nan_info> nan(n_vec);
         const int rc = ggp_group_loglik(g_, flat.data(), n_vec, S.fresh ? nullptr : carry_.data(), ll.data(), nullptr, nan.data());
-        if (rc == GGP_ERR_NAN)
+        if (rc == GGP_ERR_NAN) {
+            if (tolerate_nan) return ll;
             for (int v = 0; v < n_vec; ++v)
                 if (nan[v].cell >= 0) report_nan(S, table_, nan[v].cell, nan[v].t_index, P[v]);
+        }
         check(rc, "ggp_group_loglik");
         return ll;
     }
@@ -213,7 +219,7 @@ void record_evaluation(Session& S, const std::vector<double>& p, double tl) {
 }
 
 std::vector<double> total_likelihood(Session& S, Forest& F, const std::vector<std::vector<double>>& P, bool record = true) {
-    std::vector<double> ll = F.loglik(S, P);
+    std::vector<double> ll = F.loglik(S, P, /*tolerate_nan=*/!record);
     if (record) for (size_t v = 0; v < P.size(); ++v) record_evaluation(S, P[v], ll[v]);
     return ll;
 }
@@ -360,7 +366,11 @@ void run_minimization(Session& S, const LineageTable& T, ParameterSet& params, i
     S.save_ll = true;
     S.log << "Optimization algorithm: Nelder-Mead simplex (bounded, batched) Tolerance: " << tolerance << "\n";
     S.iteration = 0;
-    const NelderMeadResult R = nelder_mead(obj, x, lb, ub, step, tolerance, /*speculate=*/S.fresh);
+    // how many parameter vectors a speculative launch may hold: a launch over a small data set is a chain of dependent steps that
+    // costs the same for 1 or 200 vectors, over a large one every vector costs its share (4 = this iteration's candidates only)
+    int spec_batch = (int)std::min<int64_t>(192, std::max<int64_t>(4, (int64_t)4000000 / std::max<int64_t>(1, T.n_ctp())));
+    if (const char* m = getenv("GGP_B200_SPEC_BATCH")) spec_batch = std::max(1, atoi(m));
+    const NelderMeadResult R = nelder_mead(obj, x, lb, ub, step, tolerance, /*speculate=*/S.fresh, 0, spec_batch);
     S.save_ll = false;
     const double ll_max = -R.f;
     S.log << "Stopped: " << R.reason << " after " << R.evaluations << " evaluations in " << R.launches << " launches\n";

@@ -15,12 +15,19 @@
 // What is new: the objective takes a BATCH of points.  The n+1 evaluations of the initial simplex and the n
 // evaluations of a shrink are independent and go to the GPU as one launch; with `speculate` the reflection,
 // expansion and both contractions of an iteration are evaluated together as well (they depend only on the
-// simplex geometry), which turns the ~2 dependent launches per iteration into one.  Evaluation ORDER as seen by
-// the objective's log stays the sequential algorithm's.
+// simplex geometry), which turns the ~2 dependent launches per iteration into one.  With a larger `spec_batch`
+// the batch also holds the candidates of the NEXT iterations for every way the current one can end (which point is
+// accepted, which vertex is then the worst): on a small data set a launch costs the same for 1 or 200 parameter
+// vectors (one lineage tree is a chain of dependent steps), so several iterations are served by one launch.  The
+// points are looked up in a cache when the sequential algorithm asks for them; a miss costs one more launch, never
+// a different result.  Evaluation ORDER as seen by the objective's log stays the sequential algorithm's.
 #pragma once
 #include <algorithm>
 #include <cmath>
+#include <deque>
 #include <functional>
+#include <map>
+#include <set>
 #include <vector>
 
 namespace ggp {
@@ -44,7 +51,7 @@ inline bool nm_close(double a, double b) { return std::fabs(a - b) <= 1e-13 * (s
 
 inline NelderMeadResult nelder_mead(const BatchObjective& obj, std::vector<double> x0, const std::vector<double>& lb,
                                     const std::vector<double>& ub, const std::vector<double>& step, double ftol_abs,
-                                    bool speculate = false, int max_eval = 0) {
+                                    bool speculate = false, int max_eval = 0, int spec_batch = 4) {
     const int n_full = (int)x0.size();
     std::vector<int> dims;   // searched dimensions
     for (int i = 0; i < n_full; ++i) if (lb[i] != ub[i]) dims.push_back(i);
@@ -107,6 +114,84 @@ inline NelderMeadResult nelder_mead(const BatchObjective& obj, std::vector<doubl
     };
     const double alpha = 1, beta = 0.5, gamm = 2, delta = 0.5;
     auto finish = [&](const char* why) { R.x = full(best_y); R.f = best_f; R.reason = why; return R; };
+
+    // ---- speculation: candidate points of this and the following iterations, breadth first ----
+    // A hypothetical simplex: vertices with known values, and vertices accepted "in the future" whose value is unknown (NaN);
+    // maybe_worst says whether such a vertex can be the worst one (a contraction point can, a reflection / expansion point is
+    // below the second-highest value by the rule that accepted it).
+    struct Hyp {
+        std::vector<std::vector<double>> P;
+        std::vector<double> F;
+        std::vector<char> maybe_worst;
+        int depth;
+    };
+    std::map<std::vector<double>, double> cache;
+    auto collect = [&](const std::vector<std::vector<double>>& P0, const std::vector<double>& F0, const std::vector<double>& must,
+                       std::vector<std::vector<double>>& out) {
+        std::set<std::vector<double>> seen;
+        auto add = [&](const std::vector<double>& y) {
+            if ((int)out.size() >= spec_batch && !out.empty()) return;
+            if (!seen.insert(y).second || cache.count(y)) return;
+            out.push_back(y);
+        };
+        out.clear();
+        seen.insert(must);
+        out.push_back(must);
+        std::deque<Hyp> q;
+        q.push_back(Hyp{P0, F0, std::vector<char>(P0.size(), 0), 0});
+        while (!q.empty() && (int)out.size() < spec_batch) {
+            const Hyp h = q.front();
+            q.pop_front();
+            std::vector<int> worst;   // vertices that can be the highest one
+            int km = -1;
+            for (int i = 0; i <= n; ++i) {
+                if (h.F[i] == h.F[i]) { if (km < 0 || h.F[i] >= h.F[km]) km = i; }
+                else if (h.maybe_worst[i]) worst.push_back(i);
+            }
+            if (km >= 0) worst.insert(worst.begin(), km);
+            for (int hi : worst) {
+                std::vector<double> c(n, 0.0), xr, xe, xco, xci;
+                for (int i = 0; i <= n; ++i) if (i != hi) for (int j = 0; j < n; ++j) c[j] += h.P[i][j];
+                for (int j = 0; j < n; ++j) c[j] *= 1.0 / n;
+                if (!reflect(xr, c, alpha, h.P[hi])) continue;
+                const bool ok_e = reflect(xe, c, gamm, h.P[hi]), ok_co = reflect(xco, c, beta, h.P[hi]), ok_ci = reflect(xci, c, -beta, h.P[hi]);
+                add(xr);
+                if (ok_e) add(xe);
+                if (ok_co) add(xco);
+                if (ok_ci) add(xci);
+                if (h.depth + 1 >= 4) continue;
+                auto child = [&](const std::vector<double>& x, bool may_be_worst) {
+                    Hyp k = h;
+                    k.P[hi] = x;
+                    k.F[hi] = std::nan("");
+                    k.maybe_worst[hi] = may_be_worst;
+                    k.depth = h.depth + 1;
+                    q.push_back(k);
+                };
+                child(xr, false);
+                if (ok_e) child(xe, false);
+                if (ok_co) child(xco, true);
+                if (ok_ci) child(xci, true);
+            }
+        }
+    };
+    // the value the sequential algorithm asks for next: from the cache, after one batched launch if it is not there yet
+    auto need = [&](const std::vector<double>& y, const std::vector<std::vector<double>>& Pn, const std::vector<double>& Fn) {
+        auto it = cache.find(y);
+        if (it == cache.end()) {
+            std::vector<std::vector<double>> pts;
+            collect(Pn, Fn, y, pts);
+            const std::vector<double> v = eval(pts, false);
+            for (size_t k = 0; k < pts.size(); ++k) cache[pts[k]] = v[k];
+            it = cache.find(y);
+        }
+        // a speculative batch reports nothing: a point that came back NaN is evaluated again on its own as a recorded evaluation,
+        // so that the objective fails (or logs) exactly where the sequential algorithm would
+        if (it->second != it->second) return eval({y}, true)[0];
+        obj.commit(full(y), it->second);
+        ++R.evaluations;
+        return it->second;
+    };
     for (;;) {
         // order: (f, index)
         int lo = 0, hi = 0;
@@ -122,33 +207,14 @@ inline NelderMeadResult nelder_mead(const BatchObjective& obj, std::vector<doubl
         for (int i = 0; i <= n; ++i) if (i != hi) for (int j = 0; j < n; ++j) c[j] += P[i][j];
         for (int j = 0; j < n; ++j) c[j] *= 1.0 / n;
 
-        std::vector<double> xr, xe, xco, xci;
+        std::vector<double> xr, xe;
         if (!reflect(xr, c, alpha, P[hi])) return finish("xtol reached");
-        double fr, fe = 0, fco = 0, fci = 0;
-        bool have_e = false, have_co = false, have_ci = false;
-        if (speculate) {
-            std::vector<std::vector<double>> cand{xr};
-            const bool ok_e = reflect(xe, c, gamm, P[hi]), ok_co = reflect(xco, c, beta, P[hi]), ok_ci = reflect(xci, c, -beta, P[hi]);
-            if (ok_e) cand.push_back(xe);
-            if (ok_co) cand.push_back(xco);
-            if (ok_ci) cand.push_back(xci);
-            const std::vector<double> v = eval(cand, false);
-            size_t k = 0;
-            fr = v[k++];
-            if (ok_e) { fe = v[k++]; have_e = true; }
-            if (ok_co) { fco = v[k++]; have_co = true; }
-            if (ok_ci) { fci = v[k++]; have_ci = true; }
-            obj.commit(full(xr), fr);
-            ++R.evaluations;
-        } else {
-            fr = eval({xr}, true)[0];
-        }
+        double fr, fe = 0;
+        fr = speculate ? need(xr, P, F) : eval({xr}, true)[0];
         track(xr, fr);
         if (fr < F[lo]) {   // new best: try to expand
-            if (!have_e) {
-                if (!reflect(xe, c, gamm, P[hi])) return finish("xtol reached");
-                fe = eval({xe}, true)[0];
-            } else { obj.commit(full(xe), fe); ++R.evaluations; }
+            if (!reflect(xe, c, gamm, P[hi])) return finish("xtol reached");
+            fe = speculate ? need(xe, P, F) : eval({xe}, true)[0];
             track(xe, fe);
             if (fe >= fr) { P[hi] = xr; F[hi] = fr; } else { P[hi] = xe; F[hi] = fe; }
         } else if (fr < F[second]) {
@@ -157,14 +223,8 @@ inline NelderMeadResult nelder_mead(const BatchObjective& obj, std::vector<doubl
             const bool inside = F[hi] <= fr;
             std::vector<double> xc;
             double fc;
-            if (speculate && (inside ? have_ci : have_co)) {
-                xc = inside ? xci : xco; fc = inside ? fci : fco;
-                obj.commit(full(xc), fc);
-                ++R.evaluations;
-            } else {
-                if (!reflect(xc, c, inside ? -beta : beta, P[hi])) return finish("xtol reached");
-                fc = eval({xc}, true)[0];
-            }
+            if (!reflect(xc, c, inside ? -beta : beta, P[hi])) return finish("xtol reached");
+            fc = speculate ? need(xc, P, F) : eval({xc}, true)[0];
             track(xc, fc);
             if (fc < fr && fc < F[hi]) { P[hi] = xc; F[hi] = fc; }
             else {          // shrink towards the best vertex

@@ -12,6 +12,7 @@ using namespace ggp;
 
 static LineageTable g_table;
 static std::string g_text;
+static double g_nm_nan_above = HUGE_VAL;   // hcli_neldermead's objective is NaN where a coordinate exceeds this
 
 extern "C" {
 
@@ -67,11 +68,13 @@ int hcli_params(const char* file, double* final_or_null) {
 
 // Nelder-Mead on f(x) = sum_i w_i (x_i - c_i)^2 + rosenbrock coupling; logs every recorded evaluation into hcli_text()
 // as "x0 x1 ... f" lines.  Returns the number of recorded evaluations; launches and the optimum through the out arrays.
+// speculate: 0 = sequential, 1 = this iteration's candidates in one launch, k > 1 = up to k points per speculative launch
 int hcli_neldermead(int n, const double* x0, const double* lb, const double* ub, const double* step, double ftol, int speculate,
                     double* x_out, double* f_out, int* launches_out) {
     std::ostringstream rec;
     rec.precision(17);
     auto f = [&](const std::vector<double>& x) {
+        for (double xi : x) if (xi > g_nm_nan_above) return std::nan("");
         double s = 0;
         for (int i = 0; i + 1 < n; ++i) s += 100 * (x[i + 1] - x[i] * x[i]) * (x[i + 1] - x[i] * x[i]) + (1 - x[i]) * (1 - x[i]);
         return s;
@@ -91,13 +94,15 @@ int hcli_neldermead(int n, const double* x0, const double* lb, const double* ub,
     };
     obj.commit = note;
     const NelderMeadResult R = nelder_mead(obj, std::vector<double>(x0, x0 + n), std::vector<double>(lb, lb + n), std::vector<double>(ub, ub + n),
-                                           std::vector<double>(step, step + n), ftol, speculate != 0, 20000);
+                                           std::vector<double>(step, step + n), ftol, speculate != 0, 20000, speculate <= 1 ? 4 : speculate);
     std::copy(R.x.begin(), R.x.end(), x_out);
     *f_out = R.f;
     *launches_out = R.launches;
     g_text = rec.str() + R.reason;
     return R.evaluations;
 }
+
+void hcli_nm_nan_above(double v) { g_nm_nan_above = v; }
 
 void hcli_arange(double a, double b, double s, double* out, int* n) {
     const auto v = arange(a, b, s);

@@ -162,6 +162,29 @@ def test_speculative_batching_replays_the_sequential_search(hc):
     assert b[3] < 0.62 * a[3]                                             # ~1 launch per iteration instead of ~2
 
 
+def test_deep_speculation_serves_several_iterations_per_launch(hc):
+    """larger speculative batches hold the candidates of the following iterations for every way the current one can end: the
+    recorded evaluations (points, values, order) stay those of the sequential search, the launches drop; a NaN the speculation
+    meets is only reported where the sequential search evaluates that point itself"""
+    hc.hcli_nm_nan_above.argtypes = [C.c_double]
+    args = ([-1.2, 1.0, 0.5, 0.0], [-5] * 4, [5] * 4, [0.1] * 4)
+    a = run_nm(hc, *args)
+    one = run_nm(hc, *args, speculate=1)
+    two = run_nm(hc, *args, speculate=28)
+    three = run_nm(hc, *args, speculate=192)
+    for b in (one, two, three):
+        assert a[4] == b[4] and np.array_equal(a[0], b[0]) and a[2] == b[2] and a[5] == b[5]
+    assert three[3] < two[3] < one[3] and two[3] < 0.62 * one[3] and three[3] < 0.45 * one[3]
+    try:
+        hc.hcli_nm_nan_above(1.02)       # the search overshoots the optimum at (1, 1, 1, 1): some evaluations are NaN
+        s0 = run_nm(hc, *args)
+        s3 = run_nm(hc, *args, speculate=192)
+        assert any("nan" in r for r in s0[4]) and s0[4] == s3[4] and s0[2] == s3[2] and s0[5] == s3[5]
+        assert np.array_equal(s0[0], s3[0], equal_nan=True)
+    finally:
+        hc.hcli_nm_nan_above(float("inf"))
+
+
 def test_cli_without_gpu_fails_loudly(tmp_path):
     import torch
     if torch.cuda.is_available():

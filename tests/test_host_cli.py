@@ -185,6 +185,35 @@ def test_deep_speculation_serves_several_iterations_per_launch(hc):
         hc.hcli_nm_nan_above(float("inf"))
 
 
+def test_speculation_never_changes_the_search_on_random_problems(hc):
+    """random starts, steps, boxes (some active, some dimensions fixed) and NaN regions: every speculation budget replays the
+    sequential search evaluation by evaluation"""
+    hc.hcli_nm_nan_above.argtypes = [C.c_double]
+    rng = np.random.default_rng(4)
+    try:
+        for case in range(24):
+            n = int(rng.integers(2, 6))
+            x0 = rng.uniform(-2, 2, n)
+            lb = x0 - rng.uniform(0.2, 4, n)
+            ub = x0 + rng.uniform(0.2, 4, n)
+            if case % 3 == 0:
+                lb[0] = ub[0] = x0[0]            # a fixed dimension
+            if case % 4 == 0:
+                ub[-1] = min(ub[-1], 0.7)        # a bound the optimum (1, 1, ...) lies outside of
+                x0[-1] = min(x0[-1], 0.7)
+            step = rng.uniform(0.02, 0.5, n) * rng.choice([-1, 1], n)
+            hc.hcli_nm_nan_above(float(rng.uniform(1.01, 1.5)) if case % 2 else float("inf"))
+            ref = run_nm(hc, list(x0), list(lb), list(ub), list(step), ftol=1e-9)
+            for budget in (1, 9, 40, 150):
+                got = run_nm(hc, list(x0), list(lb), list(ub), list(step), ftol=1e-9, speculate=budget)
+                assert got[4] == ref[4] and got[2] == ref[2] and got[5] == ref[5], (case, budget)
+                assert np.array_equal(got[0], ref[0], equal_nan=True)
+                if case % 2 == 0:                # (a NaN the search consumes is evaluated a second time, on its own)
+                    assert got[3] <= ref[3], (case, budget)
+    finally:
+        hc.hcli_nm_nan_above(float("inf"))
+
+
 def test_cli_without_gpu_fails_loudly(tmp_path):
     import torch
     if torch.cuda.is_available():

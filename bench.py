@@ -24,7 +24,8 @@ One JSON line on stdout (rank 0).
   parity                GPU (strict and fast) against the CPU baseline's own result on the SAME trees
   cpu_baseline          the reference's math on one host core (warm-up + median of 5)
   configs               BASELINE configs[2..4] on this GPU (short runs): -p on a 1 M-cell forest, a 256-vector slice of the
-                        4096-vector scan, -j on a 100 k-cell forest with two segments
+                        4096-vector scan, -j on a 100 k-cell forest with two segments; and configs[0], the reference's example data
+                        set (evaluation latency, the command line's -m -p in the fast mode)
   strong                (N > 1) ONE 10 000-tree forest partitioned over the ranks: strong scaling of the same evaluation
 """
 import argparse
@@ -672,7 +673,53 @@ def measure_configs(ggp, _lib, lib, torch, device, fp64_peak):
                           "what": "every start point, count only (walk); records_per_s = the first %d start points with their records sorted "
                                   "on the device and copied into pinned host arrays (368 B per record)" % rows}
     f.close()
+    out["cfg1_example"] = measure_example(ggp)
     return out
+
+
+def measure_example(ggp):
+    """BASELINE configs[0], the reference's own example data set (one tree, 13 generations, 22 065 points; fixture
+    tests/golden/example_forest.npz): latency of one evaluation and of a 400-vector batch, and the command line's -m -p in the fast
+    mode (binary forest file in; the reference documents "around 5 min" for this run)"""
+    try:
+        z = np.load(os.path.join(ROOT, "tests", "golden", "example_forest.npz"))
+        data = ggp.LineageData(cell_offset=z["cell_offset"], parent=z["parent"], time=z["time"], log_length=z["log_length"], fp=z["fp"],
+                               noise_model="scaled", division_model="binomial")
+        P = np.asarray(z["params"], dtype=np.float64)
+        f = ggp.Forest(data)
+        res = {"n_ctp": int(data.n_ctp), "n_cells": int(data.n_cells), "generations": int(f.n_generations)}
+        for mode in ("strict", "fast"):
+            f.set_mode(mode)
+            for n_vec in (1, 400):
+                vecs = np.tile(P, (n_vec, 1))
+                ggp.total_likelihood(vecs, f)
+                ts = []
+                for _ in range(5):
+                    t0 = time.perf_counter()
+                    ggp.total_likelihood(vecs, f)
+                    ts.append(time.perf_counter() - t0)
+                res["%s_ms_%d_vec" % (mode, n_vec)] = float(np.median(ts)) * 1e3
+        f.close()
+        from gfp_gaussian_process_b200 import io
+        cli = os.path.join(ROOT, "gfp_gaussian_process_b200", "bin", "gfp_gaussian")
+        with tempfile.TemporaryDirectory() as tmp:
+            io.write_forest_binary(os.path.join(tmp, "example.ggpf"), data)
+            open(os.path.join(tmp, "cfg.txt"), "w").write("fp_auto = 0\n")
+            with open(os.path.join(tmp, "p.txt"), "w") as fh:   # everything free except beta, like the example's parameter file
+                for i, (name, v) in enumerate(zip(ggp.PARAM_NAMES, P)):
+                    fh.write("%s = %r\n" % (name, float(v)) if i == 6 else "%s = %r, %r\n" % (name, float(v), float(v) * 0.1))
+            t0 = time.perf_counter()
+            r = subprocess.run(["timeout", "300", cli, "-i", os.path.join(tmp, "example.ggpf"), "-b", os.path.join(tmp, "p.txt"), "-c",
+                                os.path.join(tmp, "cfg.txt"), "-m", "-p", "--fast", "-o", os.path.join(tmp, "out")], capture_output=True, text=True)
+            res["cli_minimize_predict_fast_s"] = time.perf_counter() - t0
+            res["cli_rc"] = r.returncode
+            logs = [x for x in os.listdir(os.path.join(tmp, "out")) if x.endswith(".log")] if os.path.isdir(os.path.join(tmp, "out")) else []
+            if logs:
+                text = open(os.path.join(tmp, "out", logs[0])).read()
+                res["cli_log"] = [ln for ln in text.split("\n") if ln.startswith("Stopped") or ln.startswith("Found maximum")]
+        return res
+    except Exception as e:   # an extra of the bench line: never lose the line over it
+        return {"error": repr(e)}
 
 
 if __name__ == "__main__":

@@ -456,6 +456,58 @@ def test_group_handle_shards_one_data_set_over_devices(ragged):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("ng4_min", [None, "1"])
+def test_cooperative_kernels_repeat_bit_for_bit_under_load(ng4_min, monkeypatch):
+    """Evidence in place of compute-sanitizer's racecheck, which is closed on this pool: the cooperative kernels (named barriers,
+    overlaid scratch regions, cp.async double buffer) give the SAME BITS in every repetition - per-cell sums, forward / backward /
+    combined predictions, joints - while a second thread keeps the GPU busy with other launches of the same kernels (different
+    co-residency and timing in every repetition); once with the default launch selection and once with the four-groups-per-block
+    kernels forced (GGP_B200_NG4_MIN=1).  The first repetition equals the oracle (a subset of the trees; all cells in the other
+    tests); a race in the scratch protocol would have to be invisible in 30 repetitions x 58 000 cell steps each."""
+    import threading
+    if ng4_min:
+        monkeypatch.setenv("GGP_B200_NG4_MIN", ng4_min)
+    P = ggp.PARAMS_SCALED_BINOMIAL
+    P2 = np.stack([P, P * np.array([1, 1, 1, 2, 1, 1, 1, 1, 1, 1, 1.])])
+    d = ggp.simulate_forest(300, 4, params=P, noise_model="scaled", division_model="binomial", seed=91, n_segments=2, pts_range=(9, 17))
+    load = ggp.simulate_forest(2000, 5, seed=92)
+    f, g = ggp.Forest(d), ggp.Forest(load)
+    vecs = np.stack([P, P * 1.01, P * 0.98])
+    stop = threading.Event()
+
+    def busy():
+        while not stop.is_set():
+            ggp.total_likelihood(ggp.PARAMS_CONST_GAUSS, g)
+            ggp.prediction_forward_backward(g, [ggp.PARAMS_CONST_GAUSS], forward=False, backward=False, combined=False)
+
+    t = threading.Thread(target=busy)
+    t.start()
+    try:
+        ll0, pc0 = ggp.total_likelihood(vecs, f, per_cell=True)
+        pr0 = ggp.prediction_forward_backward(f, P2)
+        j0 = ggp.collect_joint_distributions(f, P2, 1e-8, row_begin=0, row_end=400)
+        for rep in range(30):
+            ll, pc = ggp.total_likelihood(vecs, f, per_cell=True)
+            assert same_bits(pc, pc0) and same_bits(ll, ll0), rep
+            if rep % 3 == 0:
+                pr = ggp.prediction_forward_backward(f, P2)
+                for k in ("forward", "backward", "prediction"):
+                    assert same_bits(pr[k][0], pr0[k][0]) and same_bits(pr[k][1], pr0[k][1]), (rep, k)
+            if rep % 10 == 0:
+                j = ggp.collect_joint_distributions(f, P2, 1e-8, row_begin=0, row_end=400)
+                assert all(np.array_equal(a, b) for a, b in zip(j[:2], j0[:2])) and same_bits(j[2], j0[2]) and same_bits(j[3], j0[3])
+    finally:
+        stop.set()
+        t.join()
+    sub, cells, ctp = d.subset(d.roots()[:12])
+    sub.init_f, sub.init_r = d.init_stats()
+    o = Oracle(sub)
+    assert same_bits(o.total_loglik(P, per_cell=True)[1], pc0[0][cells])
+    f.close()
+    g.close()
+
+
+@pytest.mark.gpu
 def test_group_handles_come_and_go():
     """a group owns one worker thread per shard: created, used and destroyed repeatedly (also unused, and with more shards than
     trees: empty shards have no member and no work), results unchanged"""

@@ -616,6 +616,24 @@ def measure_configs(ggp, _lib, lib, torch, device, fp64_peak):
                            "e2e_ms": e2e_s * 1e3, "e2e_ctp_per_s": data.n_ctp / e2e_s, "d2h_bytes": int(3 * 14 * 8 * data.n_ctp),
                            "what": "forward + backward + combine (strict kernels); e2e = ggp_predict14: host params in, all three outputs "
                                    "as 14 doubles per time point into pinned host memory"}
+    # the north star's target line: ONE log-likelihood evaluation of this 1 M-cell forest, strict and fast (gate against strict,
+    # which equals the oracle per cell), as a fraction of the FP64 peak
+    tgt = {"n_cells": int(data.n_cells), "n_ctp": int(data.n_ctp)}
+    lls = {}
+    for mode in ("strict", "fast"):
+        f.set_mode(mode)
+        lls[mode] = float(ggp.total_likelihood(P[0], f))
+        ms = []
+        for _ in range(5):
+            ggp.total_likelihood(P[0], f)
+            ms.append(f.last_kernel_ms)
+        k = float(np.median(ms))
+        tgt[mode] = {"kernel_ms": k, "ctp_per_s": data.n_ctp / (k * 1e-3), "frac_algorithmic": data.n_ctp * F_ALG / (k * 1e-3) / 1e12 / fp64_peak,
+                     "loglik": lls[mode]}
+    tgt["fast"]["nodes"] = int(f.last_fast_nodes)
+    tgt["fast"]["strict_reruns"] = int(f.last_strict_reruns)
+    tgt["fast_vs_strict_rel"] = abs(lls["fast"] - lls["strict"]) / abs(lls["strict"])
+    out["target_1m_cells_loglik"] = tgt
     f.close()
     del pins
     # configs[3]: a 256-vector slice of the 4096-vector scan over the configs[1] forest, one ggp_loglik call, fresh mode

@@ -37,20 +37,22 @@
 
 template <class T> struct GgpFx;   // scalar helpers
 
-// Taylor coefficients 1/k!, k = 10 .. 2, of the two short exponentials below.  On the device they live in the constant bank: an
+// Taylor coefficients 1/k!, k = 15 .. 2, of the short exponentials below.  On the device they live in the constant bank: an
 // FP64 instruction reads such an operand as c[bank][offset], whereas a 64-bit literal costs two move instructions every time
 // it is materialised (the CUDA library's exp inlined once per quadrature node: 308 of the kernel's 2 712 instructions were
 // such moves, 15 % of the executed instructions; profiles/r02_fast5_gen5.txt).
-#define GGP_FEXP_INIT {0x1.27e4fb7789f5cp-22, 0x1.71de3a556c734p-19, 0x1.a01a01a01a01ap-16, 0x1.a01a01a01a01ap-13, 0x1.6c16c16c16c17p-10, \
+#define GGP_FEXP_INIT {0x1.ae7f3e733b81fp-41, 0x1.93974a8c07c9dp-37, 0x1.6124613a86d09p-33, 0x1.1eed8eff8d898p-29, 0x1.ae64567f544e4p-26, \
+                       0x1.27e4fb7789f5cp-22, 0x1.71de3a556c734p-19, 0x1.a01a01a01a01ap-16, 0x1.a01a01a01a01ap-13, 0x1.6c16c16c16c17p-10, \
                        0x1.1111111111111p-7, 0x1.5555555555555p-5, 0x1.5555555555555p-3, 0.5}
+#define GGP_FEXP_MAXDEG 15
 #if defined(__CUDACC__)
-__constant__ double ggp_fexp_c[9] = GGP_FEXP_INIT;
+__constant__ double ggp_fexp_c[14] = GGP_FEXP_INIT;
 #endif
-GGP_HDM double ggp_fexp_k(int i) {
+GGP_HDM double ggp_fexp_k(int i) {   // 1 / (GGP_FEXP_MAXDEG - i)!
 #if defined(__CUDA_ARCH__)
     return ggp_fexp_c[i];
 #else
-    constexpr double v[9] = GGP_FEXP_INIT;
+    constexpr double v[14] = GGP_FEXP_INIT;
     return v[i];
 #endif
 }
@@ -62,21 +64,23 @@ template <> struct GgpFx<double> {
     static GGP_HDM double abs_(double x) { return fabs(x); }
     static GGP_HDM bool finite_(double x) { return x - x == 0.0; }
     static GGP_HDM double ln2() { return 0.6931471805599453; }
-    // Taylor polynomial of exp of degree DEG (4 .. 10), Horner; relative truncation error |x|^(DEG+1) / (DEG+1)!
+    // Taylor polynomial of exp of degree DEG (4 .. 15), Horner; relative truncation error |x|^(DEG+1) / (DEG+1)!
     template <int DEG>
     static GGP_HDM double exp_taylor_(double x) {
-        double p = ggp_fexp_k(10 - DEG);
+        double p = ggp_fexp_k(GGP_FEXP_MAXDEG - DEG);
 #pragma unroll
-        for (int i = 11 - DEG; i < 9; ++i) p = p * x + ggp_fexp_k(i);
+        for (int i = GGP_FEXP_MAXDEG - DEG + 1; i < 14; ++i) p = p * x + ggp_fexp_k(i);
         p = p * x + 1.0;
         return p * x + 1.0;
     }
+    static GGP_HDM double exp_mid_(double x) { return exp_taylor_<15>(x); }     // |x| <= 0.5: 7e-19
     static GGP_HDM double exp_small_(double x) { return exp_taylor_<10>(x); }   // |x| <= 0.125: 3e-18
     static GGP_HDM double exp_small8_(double x) { return exp_taylor_<8>(x); }   // |x| <= 0.06: 3e-17
     static GGP_HDM double exp_tiny_(double x) { return exp_taylor_<6>(x); }     // |x| <= 0.01: 2e-18
     static GGP_HDM double exp_tiny4_(double x) { return exp_taylor_<4>(x); }    // |x| <= 0.001: 8e-18
 };
-// ranges of exp_small_ / exp_small8_ / exp_tiny_ / exp_tiny4_
+// ranges of exp_mid_ / exp_small_ / exp_small8_ / exp_tiny_ / exp_tiny4_
+#define GGP_FAST_MID 0.5
 #define GGP_FAST_SMALL 0.125
 #define GGP_FAST_SMALL8 0.06
 #define GGP_FAST_TINY 0.01
@@ -166,10 +170,11 @@ GGP_HD void ggp_fast_consts(GgpFastConsts<T, N>& K, T t, T ml, T gl, T sl2, T mq
     }
 }
 
-// the quadrature sums of one step.  LEVEL 1: the two secondary exponents (Cxl s and 2 a t s) stay below 0.01 and the main one
-// (a s^2 + B0 s) below 0.125 over the step: all three exponentials of a node are short polynomials (degrees 6 and 10); LEVEL 2:
-// below 0.001 and 0.06, degrees 4 and 8 (what real data sets and configs[1] have: growth rates of 1e-2 per minute, steps of
-// minutes); LEVEL 0: the library's exp.  Every sum is one FMA per node against a pre-multiplied constant.
+// the quadrature sums of one step.  LEVEL says which exponentials the main exponent (a s^2 + B0 s) and the two secondary ones
+// (Cxl s, 2 a t s) get over this step:  3: both tiny - main below 0.06, secondary below 0.001: Taylor degrees 8 and 4 (configs[1],
+// real data: growth rates of 1e-2 per minute, steps of minutes);  2: below 0.125 and 0.01: degrees 10 and 6;  1: below 0.5 and
+// 0.06: degrees 15 and 8 (steps of a quarter of an hour: configs[2], what a 6-node rule accepts);  0: the library's exp.
+// Every sum is one FMA per node against a pre-multiplied constant.
 template <class T, int N, int LEVEL>
 GGP_HD void ggp_fast_moments(const GgpFastConsts<T, N>& K, T a, T B0, T Cxl, T EH, T* __restrict__ M) {
     typedef GgpFx<T> X;
@@ -182,9 +187,9 @@ GGP_HD void ggp_fast_moments(const GgpFastConsts<T, N>& K, T a, T B0, T Cxl, T E
         const GgpFastNode<T> n = K.node[j];
         const T s = n.s;
         const T xa = a * n.s2 + B0 * s, xv = Cxl * s, xu = twoat * s;
-        const T A = LEVEL == 2 ? X::exp_small8_(xa) : LEVEL == 1 ? X::exp_small_(xa) : X::exp_(xa);   // exp(a s^2 + B0 s)
-        const T V = LEVEL == 2 ? X::exp_tiny4_(xv) : LEVEL == 1 ? X::exp_tiny_(xv) : X::exp_(xv);
-        const T U = LEVEL == 2 ? X::exp_tiny4_(xu) : LEVEL == 1 ? X::exp_tiny_(xu) : X::exp_(xu);
+        const T A = LEVEL == 3 ? X::exp_small8_(xa) : LEVEL == 2 ? X::exp_small_(xa) : LEVEL == 1 ? X::exp_mid_(xa) : X::exp_(xa);   // exp(a s^2 + B0 s)
+        const T V = LEVEL == 3 ? X::exp_tiny4_(xv) : LEVEL == 2 ? X::exp_tiny_(xv) : LEVEL == 1 ? X::exp_small8_(xv) : X::exp_(xv);
+        const T U = LEVEL == 3 ? X::exp_tiny4_(xu) : LEVEL == 2 ? X::exp_tiny_(xu) : LEVEL == 1 ? X::exp_small8_(xu) : X::exp_(xu);
         const T AW = A * V;                                    // exp(a s^2 + W s), W = B0 + Cxl
         const T H = AW * (U * EH);                             // exp(a s'^2 + W s'), s' = t + s, EH = exp(t (W + a t))
         MB0 += n.w * A; MB1 += n.ws * A;
@@ -220,21 +225,24 @@ GGP_HD bool ggp_fast_propagate(GgpFastState<T>& st, const GgpFastConsts<T, N>& K
     // lam t bounds |a s^2 + B s| on [0, t] and |t (W + a t)|: below GGP_FAST_SMALL (every step a rule of at most 5 nodes accepts)
     // these exponentials are short polynomials as well
     const T sec = X::abs_(Cxl) > T(2) * a * t ? X::abs_(Cxl) : T(2) * a * t;
-    const bool small = lam * t <= T(GGP_FAST_SMALL);
     // the exponents the polynomials see: |a s^2 + B s| <= (|B| + |a| t) t on [0, t] and |t (W + a t)| (gq lives in the weights)
     const T xmain = ((X::abs_(B0) > X::abs_(W) ? X::abs_(B0) : X::abs_(W)) + X::abs_(a) * t) * t;
-    const int level = !small ? 0 : (xmain <= T(GGP_FAST_SMALL8) && sec * t <= T(GGP_FAST_TINY4)) ? 2 : (sec * t <= T(GGP_FAST_TINY) ? 1 : 0);
+    const T xsec = sec * t;
+    const int level = !(xmain <= T(GGP_FAST_MID) && xsec <= T(GGP_FAST_SMALL8)) ? 0
+                      : (xmain <= T(GGP_FAST_SMALL8) && xsec <= T(GGP_FAST_TINY4)) ? 3
+                      : (xmain <= T(GGP_FAST_SMALL) && xsec <= T(GGP_FAST_TINY)) ? 2 : 1;
     const T xh = t * (W + a * t);
-    const T EH = level == 2 ? X::exp_small8_(xh) : small ? X::exp_small_(xh) : X::exp_(xh);
+    const T EH = level == 3 ? X::exp_small8_(xh) : level == 2 ? X::exp_small_(xh) : level == 1 ? X::exp_mid_(xh) : X::exp_(xh);
     T M[19];
-    if (level == 2) ggp_fast_moments<T, N, 2>(K, a, B0, Cxl, EH, M);
+    if (level == 3) ggp_fast_moments<T, N, 3>(K, a, B0, Cxl, EH, M);
+    else if (level == 2) ggp_fast_moments<T, N, 2>(K, a, B0, Cxl, EH, M);
     else if (level == 1) ggp_fast_moments<T, N, 1>(K, a, B0, Cxl, EH, M);
     else ggp_fast_moments<T, N, 0>(K, a, B0, Cxl, EH, M);
     // exp(c): c0 = bx + Cxx/2 - b t (B-family, mean_cov_model.h:76-115), c5 = 2 (bx + Cxx - b t) (W-family, :124-164)
     const T E1 = X::exp_(bx + T(0.5) * Cxx);
     const T Ec0 = E1 * K.ebt;
     const T aCxx = X::abs_(Cxx);
-    const T Ec5 = (E1 * K.ebt) * (E1 * K.ebt) * (aCxx <= T(GGP_FAST_TINY) ? X::exp_tiny_(Cxx) : aCxx <= T(GGP_FAST_SMALL) ? X::exp_small_(Cxx) : X::exp_(Cxx));
+    const T Ec5 = (E1 * K.ebt) * (E1 * K.ebt) * (aCxx <= T(GGP_FAST_TINY) ? X::exp_tiny_(Cxx) : aCxx <= T(GGP_FAST_MID) ? X::exp_mid_(Cxx) : X::exp_(Cxx));
     const T JB0 = Ec0 * M[0], JB1 = Ec0 * M[1];                        // I_k(B0, c0; 0, t)
     const T JBm0 = Ec0 * M[2], JBm1 = Ec0 * M[3], JBm2 = Ec0 * M[4];   // I_k(B0 - gq, c0; 0, t)
     const T JBs0 = Ec0 * M[5];                                         // I_0(B0 + gq, c0) - I_0(B0 - gq, c0)

@@ -14,6 +14,7 @@
 typedef __float128 quad;
 template <> struct GgpFx<quad> {
     static quad exp_(quad x) { return expq(x); }
+    static quad exp_mid_(quad x) { return expq(x); }
     static quad exp_small_(quad x) { return expq(x); }
     static quad exp_small8_(quad x) { return expq(x); }
     static quad exp_tiny_(quad x) { return expq(x); }

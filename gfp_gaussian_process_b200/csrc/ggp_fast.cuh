@@ -228,9 +228,16 @@ GGP_HD bool ggp_fast_propagate(GgpFastState<T>& st, const GgpFastConsts<T, N>& K
     // the exponents the polynomials see: |a s^2 + B s| <= (|B| + |a| t) t on [0, t] and |t (W + a t)| (gq lives in the weights)
     const T xmain = ((X::abs_(B0) > X::abs_(W) ? X::abs_(B0) : X::abs_(W)) + X::abs_(a) * t) * t;
     const T xsec = sec * t;
-    const int level = !(xmain <= T(GGP_FAST_MID) && xsec <= T(GGP_FAST_SMALL8)) ? 0
-                      : (xmain <= T(GGP_FAST_SMALL8) && xsec <= T(GGP_FAST_TINY4)) ? 3
-                      : (xmain <= T(GGP_FAST_SMALL) && xsec <= T(GGP_FAST_TINY)) ? 2 : 1;
+    int level = !(xmain <= T(GGP_FAST_MID) && xsec <= T(GGP_FAST_SMALL8)) ? 0
+                : (xmain <= T(GGP_FAST_SMALL8) && xsec <= T(GGP_FAST_TINY4)) ? 3
+                : (xmain <= T(GGP_FAST_SMALL) && xsec <= T(GGP_FAST_TINY)) ? 2 : 1;
+#if defined(__CUDA_ARCH__)
+    // the levels are nested (a lower one is valid wherever a higher one is): the lanes of a warp take the lowest level any of
+    // them needs, so that a warp runs ONE variant of the sums.  Rules of 6 nodes and more only: their steps straddle the 0.125
+    // threshold (configs[2]: 40 % of the warps ran two variants, 1.04 -> 0.93 ms); a 5-node rule accepts no exponent above 0.12
+    // and the reduction costs 4 % where the lanes agree anyway (configs[1]: 0.592 vs 0.569 ms)
+    if (N >= 6) level = __reduce_min_sync(__activemask(), level);
+#endif
     const T xh = t * (W + a * t);
     const T EH = level == 3 ? X::exp_small8_(xh) : level == 2 ? X::exp_small_(xh) : level == 1 ? X::exp_mid_(xh) : X::exp_(xh);
     T M[19];

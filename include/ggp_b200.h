@@ -153,7 +153,8 @@ int ggp_predict14(ggp_forest* f, const double* params, int32_t n_seg,
  * Rows are the start points row_begin <= ctp < row_end, so a caller can stream the matrix in row blocks like the
  * reference streams lines (the dense row of the example data set alone is 22 065 x 44 fields).  Requires a prior
  * ggp_predict on the handle with the same params.  *out_count receives the number of joints the rows hold; at most
- * `cap` are written (call with cap = 0 to size the buffers). */
+ * `cap` are written (call with cap = 0 to size the buffers).  The call's device scratch (about 800 bytes per record) stays with
+ * the handle for the next call as long as it is below 6 GB, and goes with ggp_forest_destroy. */
 int ggp_joints(ggp_forest* f, const double* params, int32_t n_seg, double rel_tol, int64_t row_begin, int64_t row_end,
                int64_t cap, int64_t* out_count, int64_t* row_ctp, int64_t* col_ctp, double* rec44);
 
@@ -168,6 +169,8 @@ int ggp_joints(ggp_forest* f, const double* params, int32_t n_seg, double rel_to
  *                           per-block partials added in long double; each entry is the leading double of its sum,
  *   out_sums_lo             NULL or [n_bins][50]: the remainder (sum - leading double),
  *   out_joints              NULL or the number of joints the walk emitted.
+ * The joints are walked in row blocks whose records stay on the device; their buffers (a quarter of the free device memory,
+ * at most 16 GB, by default) stay with the handle until ggp_forest_destroy.
  * Requires a prior ggp_predict with the same params, fewer than 65 535 bins, and parents stored before their daughters (else
  * GGP_ERR_BAD_ARG: reduce the sparse records of ggp_joints on the host, host/ggp_correlation.hpp). */
 int ggp_correlation_sums(ggp_forest* f, const double* params, int32_t n_seg, double rel_tol, double dt_step, int32_t n_bins,
